@@ -1,0 +1,138 @@
+/* chi^2(c1, c2) objective of the per-conformation fit and its analytic gradient.
+ *
+ * Follows src/min_saxs.c operation for operation: sxs_best_scale (:261-319) gives the optimal linear
+ * scale k for the trial (c1, c2), gradient() (:3-105) then accumulates f and df/dc with k frozen.
+ * Both walk the q nodes once with a piecewise-linear model between nodes (q_{-1} = -1).
+ * The six cross terms are read through a stride so that a warp's loads are coalesced
+ * (layout X[(q*6 + c) * stride + point]); the peak rescale of sxs_fit_params (:170-188) is applied
+ * on the fly as x*scale, which rounds exactly like the reference's in-place `*= scale`.
+ *
+ * Compiled with -fmad=false (see lbfgsb_n2m3.h); plain C so the CPU tests can include it.
+ */
+#ifndef SXS_FIT_EVAL_H
+#define SXS_FIT_EVAL_H
+
+#include <math.h>
+
+#ifndef SXS_HD
+#ifdef __CUDACC__
+#define SXS_HD __host__ __device__ __forceinline__
+#else
+#define SXS_HD static inline
+#endif
+#endif
+
+struct sxs_fit_ctx {
+	const double *x;      /* cross terms of this point: x[(q*6 + c) * stride] */
+	long stride;
+	const double *a;      /* compressed experiment, a[q*6 + 0..5] (src/min_saxs.c:353-389) */
+	const double *qvals;
+	int qnum;
+	double mult;          /* (4pi/3)^(3/2) rm^2 / (16 pi), src/min_saxs.c:121 */
+	double scale;         /* peak / I(0) rescale, src/min_saxs.c:170-179 */
+};
+
+enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
+
+#define SXS_X(ctx, q, c) ((ctx)->x[((long)(q) * 6 + (c)) * (ctx)->stride] * (ctx)->scale)
+
+/* src/min_saxs.c:261-319 */
+SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, double c2)
+{
+	const double *a = ctx->a;
+	const double *q = ctx->qvals;
+	const double mult = ctx->mult;
+	const double corr = -mult * (c1 * c1 - 1.0);
+	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
+
+	double in_prev = SXS_X(ctx, 0, SXS_VV) - G * SXS_X(ctx, 0, SXS_VD) + c2 * SXS_X(ctx, 0, SXS_VW) +
+	                 G * G * SXS_X(ctx, 0, SXS_DD) - G * c2 * SXS_X(ctx, 0, SXS_DW) + c2 * c2 * SXS_X(ctx, 0, SXS_WW);
+	const double c1_cube = c1 * c1 * c1;
+	double q_prev = -1.0;
+	double up = 0.0, down = 0.0;
+
+	for (int i = 0; i < ctx->qnum; i++) {
+		const double q_cur = q[i];
+		G = c1_cube * exp(corr * q_cur * q_cur);
+		const double in = SXS_X(ctx, i, SXS_VV) - G * SXS_X(ctx, i, SXS_VD) + c2 * SXS_X(ctx, i, SXS_VW) +
+		                  G * G * SXS_X(ctx, i, SXS_DD) - G * c2 * SXS_X(ctx, i, SXS_DW) +
+		                  c2 * c2 * SXS_X(ctx, i, SXS_WW);
+		const double tan = (in - in_prev) / (q_cur - q_prev);
+		const double buf = in - tan * q_cur;
+
+		up += buf * a[i * 6 + 1] + tan * a[i * 6 + 2];
+		down += buf * buf * a[i * 6 + 3] + 2.0 * tan * buf * a[i * 6 + 4] + tan * tan * a[i * 6 + 5];
+
+		in_prev = in;
+		q_prev = q_cur;
+	}
+	return up / down;
+}
+
+/* src/min_saxs.c:3-105 with k = sxs_best_scale(c1, c2) as the driver loop sets it (:233-236). */
+SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, double *f, double *g0, double *g1)
+{
+	const double k = sxs_fit_best_scale(ctx, c1, c2);
+	const double *a = ctx->a;
+	const double *q = ctx->qvals;
+	const double mult = ctx->mult;
+
+	double grad0 = 0.0, grad1 = 0.0;
+	const double corr = -mult * (c1 * c1 - 1.0);
+	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
+	double G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q[0] * q[0]);
+
+	double in_prev = SXS_X(ctx, 0, SXS_VV) - G * SXS_X(ctx, 0, SXS_VD) + c2 * SXS_X(ctx, 0, SXS_VW) +
+	                 G * G * SXS_X(ctx, 0, SXS_DD) - G * c2 * SXS_X(ctx, 0, SXS_DW) + c2 * c2 * SXS_X(ctx, 0, SXS_WW);
+	double in_der_c1_prev = -G_der * SXS_X(ctx, 0, SXS_VD) + 2.0 * G * G_der * SXS_X(ctx, 0, SXS_DD) -
+	                        G_der * c2 * SXS_X(ctx, 0, SXS_DW);
+	double in_der_c2_prev = SXS_X(ctx, 0, SXS_VW) - G * SXS_X(ctx, 0, SXS_DW) + 2.0 * c2 * SXS_X(ctx, 0, SXS_WW);
+
+	double q_prev = -1.0;
+	double score = 0.0;
+	const double c1_cube = c1 * c1 * c1;
+
+	for (int i = 0; i < ctx->qnum; i++) {
+		const double q_cur = q[i];
+		G = c1_cube * exp(corr * q_cur * q_cur);
+		G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q_cur * q_cur);
+
+		const double xvv = SXS_X(ctx, i, SXS_VV), xvd = SXS_X(ctx, i, SXS_VD), xvw = SXS_X(ctx, i, SXS_VW);
+		const double xdd = SXS_X(ctx, i, SXS_DD), xdw = SXS_X(ctx, i, SXS_DW), xww = SXS_X(ctx, i, SXS_WW);
+
+		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
+		const double in_der_c1 = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);
+		const double in_der_c2 = xvw - G * xdw + 2.0 * c2 * xww;
+
+		double buf = 1.0 / (q_cur - q_prev);
+		const double tan = (in - in_prev) * buf;
+		const double tan_c1_der = (in_der_c1 - in_der_c1_prev) * buf;
+		const double tan_c2_der = (in_der_c2 - in_der_c2_prev) * buf;
+
+		const double a1 = a[i * 6 + 1], a2 = a[i * 6 + 2], a3 = a[i * 6 + 3], a4 = a[i * 6 + 4], a5 = a[i * 6 + 5];
+
+		grad0 += 2.0 * k * (-(in_der_c1 - tan_c1_der * q_cur) * a1 - tan_c1_der * a2 +
+		                    k * ((in - tan * q_cur) * (in_der_c1 - tan_c1_der * q_cur) * a3 +
+		                         (in * tan_c1_der + in_der_c1 * tan - 2.0 * tan * tan_c1_der * q_cur) * a4 +
+		                         tan * tan_c1_der * a5));
+
+		grad1 += 2.0 * k * (-(in_der_c2 - tan_c2_der * q_cur) * a1 - tan_c2_der * a2 +
+		                    k * ((in - tan * q_cur) * (in_der_c2 - tan_c2_der * q_cur) * a3 +
+		                         (in * tan_c2_der + in_der_c2 * tan - 2.0 * tan * tan_c2_der * q_cur) * a4 +
+		                         tan * tan_c2_der * a5));
+
+		buf = in - tan * q_cur;
+		score += a[i * 6] + k * (-2.0 * buf * a1 - 2.0 * tan * a2 +
+		                         k * (buf * buf * a3 + 2.0 * buf * tan * a4 + tan * tan * a5));
+
+		in_prev = in;
+		in_der_c1_prev = in_der_c1;
+		in_der_c2_prev = in_der_c2;
+		q_prev = q_cur;
+	}
+	*g0 = grad0;
+	*g1 = grad1;
+	*f = score;
+}
+
+#endif /* SXS_FIT_EVAL_H */
