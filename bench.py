@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — conformations scored per second by the FFT-SAXS `correlate` scoring path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Product arm.  Workload = BASELINE.json configs[2]: synthetic 3000-atom receptor + 1500-atom ligand, L=15, 50 q
+points, 70 000 rotations x 64 z steps = 4.48 M poses per GPU (weak scaling: every rank scores its own pose list
+of that size, as if the ft files were dealt out; the score tables are all-gathered over NCCL inside the step).
+One step = one full pass of sxs_compute_saxs_scores' work over the batch: key sort -> distinct grid points ->
+z-translation -> cross terms (K3) -> (c1,c2) fit (K4) -> scatter.
+  value : poses/s with the pose list, coefficient tables and outputs resident in HBM (C-ABI *_dev entry),
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e   : poses/s through the reference-shaped API (sxs_compute_saxs_scores via its flat adapter) with pinned
+          HOST buffers in and out — H2D/D2H, the host Bessel table and the host scatter are inside the timing.
+Reference arm (--impl reference): the reference's own CPU code (oracle/_ref/libsxsref.so = its unmodified
+sources) on the host cores, one process per core over z like its MPI build, on a bounded sample of the same poses.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+WORKLOAD = "cfg3_3k+1.5k_L15_Q50_70kx64z"
+METRIC = "dimer conformations scored/sec (correlate)"
+UNIT = "conformations/s"
+
+
+def env_int(name, dflt):
+    try:
+        return int(os.environ.get(name, dflt))
+    except ValueError:
+        return dflt
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for (t, l) in self.lines:
+            if t < t0 or t > t1 + 0.3:
+                continue
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- workload
+
+def build_inputs(expand, opt_params, seed_rank, nrot, nz):
+    """molecules identical on every rank, pose list seeded per rank"""
+    from libfmftsaxs_b200 import workload as wl
+    w = wl.make(WORKLOAD, nrot=nrot, nz=nz)
+    if seed_rank:
+        w["index"] = wl.make_pose_indices(w["L"], w["zvals"], nrot or wl.CONFIGS[WORKLOAD]["nrot"],
+                                          w["seed"] + 3 + 1000 * seed_rank)
+    q, L = w["qvals"], w["L"]
+    coefA, rmA, _ = expand(wl.MAP_PATH, w["rec"]["xyz"], w["rec"]["res"], w["rec"]["atm"], w["rec"]["radius"], q, L,
+                           sa=w["rec"]["sa"], water_mode=1)
+    coefB, rmB, _ = expand(wl.MAP_PATH, w["lig"]["xyz"], w["lig"]["res"], w["lig"]["atm"], w["lig"]["radius"], q, L,
+                           sa=w["lig"]["sa"], water_mode=1)
+    eq, ei, ee = wl.experimental_curve(coefA, coefB, q)
+    a, scal = opt_params(eq, ei, ee, q, wl.mean_radius(w["rec"], w["lig"]))
+    w.update(coefA=coefA, coefB=coefB, a=a, scal=scal)
+    return w
+
+
+def sample_slabs(index, L, nslabs, seed=7):
+    """Bounded sample for the CPU arm: all poses of `nslabs` randomly chosen (z, beta2) slabs, i.e. up to L+1
+    complete (z, b1, b2) cells each.  The reference's cost is per cell plus one ligand pre-sum per slab, so whole
+    slabs keep its amortisation as in a full run.  Returns one row-index array per slab."""
+    nb, N = L + 1, 2 * L + 1
+    v = index.astype(np.int64) // (N ** 3)          # (z*nb + b1)*nb + b2
+    slab = (v // (nb * nb)) * nb + (v % nb)          # z*nb + b2
+    u = np.unique(slab)
+    rng = np.random.default_rng(seed)
+    pick = rng.choice(u, size=min(nslabs, len(u)), replace=False)
+    return [np.flatnonzero(slab == s) for s in pick]
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def _ref_worker(job):
+    import refso
+    idx, w = job
+    t = time.perf_counter()
+    refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], w["zvals"], w["L"])
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    import refso
+    if not refso.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsxsref.so missing (built from /root/reference by oracle/Makefile)"}))
+        return 0
+    from multiprocessing import Pool
+    w = build_inputs(refso.expand, refso.opt_params, 0, args.nrot, args.nz)
+    L = w["L"]
+    N = 2 * L + 1
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.ref_procs or cores))
+    # bounded sample: one (z, beta2) slab per process — the processes work on different z like the MPI ranks of
+    # tools/correlate.c:142-147, each paying the full per-call set-up (tables, allocations) like a rank does
+    shards = [w["index"][r] for r in sample_slabs(w["index"], L, procs * args.ref_slabs_per_proc)]
+    shards = [np.concatenate(shards[i::procs]) for i in range(min(procs, len(shards)))]
+    idx = np.concatenate(shards)
+    small = {k: w[k] for k in ("coefA", "coefB", "a", "scal", "qvals", "zvals", "L")}
+    times = []
+    with Pool(len(shards)) as pool:
+        for it in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            pool.map(_ref_worker, [(s, small) for s in shards])
+            dt = time.perf_counter() - t
+            if it >= args.warmup:
+                times.append(dt)
+    tot = sum(times)
+    value = len(idx) * len(times) / tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "poses_in_sample": int(len(idx)), "cells_in_sample": int(len(np.unique(idx.astype(np.int64) // N ** 3))),
+                       "L": L, "qnum": len(w["qvals"])},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": len(shards), "kind": "reference",
+                             "sample": "all poses of %d random (z,beta2) slabs (each up to L+1 complete cells) of the workload, one "
+                                       "slab per process, %d processes; reference sources unmodified, FFTW replaced by a "
+                                       "split-radix-free DFT shim (oracle/shim/fftw_shim.c)" % (procs * args.ref_slabs_per_proc, len(shards))},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- product arm
+
+def run_product(args):
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    os.environ["SXS_CUDA_DEVICES"] = str(local)
+    import torch
+    import torch.distributed as dist
+    from libfmftsaxs_b200 import capi
+
+    if not torch.cuda.is_available() or capi.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = build_inputs(capi.expand, capi.opt_params, rank, args.nrot, args.nz)
+    L, q, zvals, idx = w["L"], w["qvals"], w["zvals"], w["index"]
+    n = len(idx)
+    plan = capi.Plan(L, q, device=local)
+    plan.set_molecules(w["coefA"], w["coefB"])
+    plan.set_experiment(w["a"], w["scal"][1], w["scal"][2])
+    plan.set_translations(zvals)
+
+    is64 = idx.dtype == np.int64
+    d_idx = torch.from_numpy(idx).to(dev)
+    d_out = torch.zeros((3, n), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world, 3, n), dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.score_device(d_idx.data_ptr(), n, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), stream, i64=is64)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    plan.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    ktimes = plan.kernel_times()
+    plan.set_profiling(False)
+    stats = plan.stats()
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the reference-shaped API with host buffers ----
+    h_idx = torch.from_numpy(idx).pin_memory()
+    h_out = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    import ctypes as C
+    lib = capi.lib()
+    dp = C.POINTER(C.c_double)
+    cA, cB, a_, sc_, q_, z_ = [np.ascontiguousarray(x, dtype=np.float64) for x in (w["coefA"], w["coefB"], w["a"], w["scal"], q, zvals)]
+
+    def e2e_step():
+        args_tail = (capi.dptr(cA), capi.dptr(cB), capi.dptr(a_), capi.dptr(sc_), capi.dptr(q_), C.c_int(len(q_)),
+                     capi.dptr(z_), C.c_int(len(z_)), C.c_int(L), C.c_int(1))
+        o = [C.cast(t.data_ptr(), dp) for t in h_out]
+        if is64:
+            lib.sxs_flat_scores64(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_longlong)), C.c_longlong(n), *args_tail)
+        else:
+            lib.sxs_flat_scores(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_int)), C.c_int(n), *args_tail)
+        return float(h_out[0][0])
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    te = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - te
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * n * e2e_steps / e2e_s
+    N = 2 * L + 1
+    h2d = idx.nbytes + cA.nbytes + cB.nbytes + a_.nbytes + len(z_) * len(q_) * N * 8
+    d2h = n * (3 * 8 + 4)
+
+    # parity spot check of what was just timed: resident path == host path (same kernels), finite, in the box
+    same = bool(np.array_equal(d_out[0].cpu().numpy(), h_out[0].numpy()))
+
+    line = None
+    if rank == 0:
+        ML = (L + 1) * (L + 2) // 2
+        Q = len(q)
+        flops_per_point = Q * (9 * ML * 8 + (L + 1) * 6 * 4)
+        cross_ms, cross_n = ktimes["cross"]
+        fp64_peak = capi.fp64_peak(local)
+        ach = stats["points"] * args.steps * flops_per_point / (cross_ms * 1e-3) / 1e12 if cross_ms > 0 else None
+        bytes_per_point = 2 * 3 * ML * 16 * Q  # one receptor row + one ligand row element per (c, m, l, q)
+        roofline = {"kernel": "k_cross (K3: angular transform + cross terms)", "bound": "fp64",
+                    "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": (ach / fp64_peak) if ach else None,
+                    "traffic": None,
+                    "peak_source": "DFMA microbenchmark run by this bench (MEASURED_PEAKS.json has no FP64 entry)",
+                    "flops_per_launch": stats["points"] * flops_per_point / max(1, cross_n // args.steps),
+                    "avg_launch_ms": cross_ms / max(1, cross_n),
+                    "l2_side_gbs": stats["points"] * args.steps * bytes_per_point / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else None}
+        cpu = cpu_baseline(w, args)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "poses_per_gpu": int(n), "distinct_grid_points": int(stats["points"]),
+                           "L": L, "qnum": Q, "z_steps": int(len(zvals)), "rec_atoms": len(w["rec"]["res"]),
+                           "lig_atoms": len(w["lig"]["res"]),
+                           "l2_policy": "inputs larger than L2 (rotated tables 324 MB + translated slabs %.1f GB per step)" % (stats["slabs"] * Q * 3 * ML * N * 16 / 1e9)},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "api": "sxs_compute_saxs_scores (flat adapter), pinned host buffers"},
+                "gpu_launches": int(stats["launches"] * args.steps),
+                "kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
+                "roofline": roofline, "cpu_baseline": cpu, "resident_equals_host_path": same}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline(w, args):
+    """the compiled reference on ONE host core over a bounded sample of the same poses (rank 0, N=1 only)"""
+    if env_int("WORLD_SIZE", 1) != 1 or args.no_cpu_baseline:
+        return None
+    import refso
+    if not refso.available():
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    idx = np.concatenate([w["index"][r] for r in sample_slabs(w["index"], w["L"], args.cpu_slabs)])
+    t = time.perf_counter()
+    refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], w["zvals"], w["L"])
+    dt = time.perf_counter() - t
+    return {"value": len(idx) / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
+            "sample": "all %d poses of %d random (z,beta2) slab(s) of the workload (up to L+1 complete cells each); "
+                      "unmodified reference sources, FFTW replaced by the DFT shim" % (len(idx), args.cpu_slabs)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nrot", type=int, default=None, help="override rotations per z (default 70000)")
+    ap.add_argument("--nz", type=int, default=None, help="override number of z steps (default 64)")
+    ap.add_argument("--cpu-slabs", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-slabs-per-proc", type=int, default=1)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,47 @@
+/* Internal declarations shared by the CUDA translation units (sm_100a only). */
+#ifndef SXS_DEV_CUH
+#define SXS_DEV_CUH
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "sxs_cuda.h"
+
+extern "C" void sxs_cuda_set_error(const char *fmt, ...);
+
+#define SXS_CK(call)                                                                                   \
+	do {                                                                                               \
+		cudaError_t e_ = (call);                                                                       \
+		if (e_ != cudaSuccess) {                                                                       \
+			sxs_cuda_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			return -1;                                                                                 \
+		}                                                                                              \
+	} while (0)
+
+#define SXS_CK_LAUNCH()                                                                               \
+	do {                                                                                              \
+		cudaError_t e_ = cudaGetLastError();                                                          \
+		if (e_ != cudaSuccess) {                                                                      \
+			sxs_cuda_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+			return -1;                                                                                \
+		}                                                                                             \
+	} while (0)
+
+/* number of (m, l) pairs with 0 <= m <= l <= L, and the packed index of one */
+__host__ __device__ inline int sxs_ml_count(int L) { return (L + 1) * (L + 2) / 2; }
+__host__ __device__ inline int sxs_ml_index(int L, int m, int l) { return m * (L + 1) - m * (m - 1) / 2 + (l - m); }
+
+/* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
+
+/* K4: one fit per point.  x: cross terms, x[(q*6 + k)*stride + p]; res[p*4] = chi, c1, c2, evaluations. */
+int sxs_launch_fit(const double *d_x, long long stride, long long npts, const double *d_a, const double *d_qvals,
+                   int qnum, double mult, double peak, int rescale, double *d_res, cudaStream_t stream);
+
+/* Self terms of the pair (A, B) in comp_const_int order (src/fftsaxs.c:27-50,638-643); out[k*qnum + q],
+ * VD/VW/DW already doubled as fill_const applies them (src/fftsaxs.c:76-81). */
+int sxs_launch_pair_const(const double *d_coefA, const double *d_coefB, int qnum, int L, double *d_out,
+                          cudaStream_t stream);
+
+#endif

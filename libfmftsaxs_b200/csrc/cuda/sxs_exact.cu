@@ -1,0 +1,264 @@
+/* Kernels whose arithmetic must follow the reference operation for operation; this translation
+ * unit is compiled with -fmad=false so that nvcc never fuses a multiply into an add.
+ *
+ *   k_fit            K4, the fused per-conformation (c1, c2) fit: peak rescale + L-BFGS-B + sqrt(f)
+ *                    (src/min_saxs.c:153-259 and the vendored lbfgsb/src/ of the reference)
+ *   k_fit_eval       best scale / objective / gradient at one point (src/min_saxs.c:3-105,261-319)
+ *   k_pair_const     I_A + I_B self terms (src/fftsaxs.c:27-50)
+ *   k_self_terms     six self cross terms of one molecule (src/min_saxs.c:437-499)
+ *   k_profile        I(q) of one molecule (src/profile.c:186-233)
+ *
+ * K4 roofline: FP64 pipe.  Per objective evaluation a thread does qnum*(~190 flops + 2 exp) and re-reads
+ * its 6*qnum cross terms (coalesced across the warp, L2-resident); 7-13 evaluations per fit on real data.
+ */
+#include <math.h>
+
+#include "sxs_dev.cuh"
+
+#define SXS_HD __host__ __device__ __forceinline__
+#include "fit_point.h"
+
+#define SXS_FIT_MAXQ 512
+
+__global__ void __launch_bounds__(128)
+k_fit(const double *__restrict__ x, long long stride, long long npts, const double *__restrict__ a,
+      const double *__restrict__ qvals, int qnum, double mult, double peak, int rescale, double *__restrict__ res)
+{
+	extern __shared__ double s_tab[]; /* [6*qnum] moments, then [qnum] q grid */
+	double *s_a = s_tab;
+	double *s_q = s_tab + 6 * qnum;
+	for (int i = threadIdx.x; i < 6 * qnum; i += blockDim.x) {
+		s_a[i] = a[i];
+	}
+	for (int i = threadIdx.x; i < qnum; i += blockDim.x) {
+		s_q[i] = qvals[i];
+	}
+	__syncthreads();
+
+	const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= npts) {
+		return;
+	}
+	double score, c1, c2;
+	int nfg;
+	if (rescale) {
+		sxs_fit_point(x + p, stride, s_a, s_q, qnum, mult, peak, &score, &c1, &c2, &nfg);
+	} else {
+		/* sxs_lbfgs_fitting on cross terms as given: a unit rescale factor */
+		struct sxs_fit_ctx ctx;
+		ctx.x = x + p; ctx.stride = stride; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
+		const double i0 = ctx.x[0 * stride] + ctx.x[3 * stride] + ctx.x[5 * stride] + ctx.x[2 * stride] -
+		                  ctx.x[1 * stride] - ctx.x[4 * stride];
+		/* peak := I(0) makes scale exactly 1.0 */
+		sxs_fit_point(x + p, stride, s_a, s_q, qnum, mult, i0, &score, &c1, &c2, &nfg);
+	}
+	res[p * 4 + 0] = score;
+	res[p * 4 + 1] = c1;
+	res[p * 4 + 2] = c2;
+	res[p * 4 + 3] = (double)nfg;
+}
+
+int sxs_launch_fit(const double *d_x, long long stride, long long npts, const double *d_a, const double *d_qvals,
+                   int qnum, double mult, double peak, int rescale, double *d_res, cudaStream_t stream)
+{
+	if (npts <= 0) {
+		return 0;
+	}
+	if (qnum > SXS_FIT_MAXQ) {
+		sxs_cuda_set_error("qnum %d exceeds %d", qnum, SXS_FIT_MAXQ);
+		return -1;
+	}
+	const int threads = 128;
+	const long long blocks = (npts + threads - 1) / threads;
+	k_fit<<<(unsigned)blocks, threads, sizeof(double) * 7 * qnum, stream>>>(d_x, stride, npts, d_a, d_qvals, qnum,
+	                                                                         mult, peak, rescale, d_res);
+	SXS_CK_LAUNCH();
+	return 0;
+}
+
+/* cross[(p*6 + k)*qnum + q]  ->  x[(q*6 + k)*npts + p] */
+__global__ void k_cross_to_strided(const double *__restrict__ cross, long long npts, int qnum, double *__restrict__ x)
+{
+	const long long total = npts * 6 * qnum;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+		const long long p = i % npts;
+		const long long qk = i / npts;
+		const int k = (int)(qk % 6);
+		const int q = (int)(qk / 6);
+		x[i] = cross[(p * 6 + k) * qnum + q];
+	}
+}
+
+extern "C" int sxs_cuda_fit_profiles(int device, const double *cross, long long npts, const double *a,
+                                     const double *qvals, int qnum, double mult, double peak, int rescale, double *out)
+{
+	if (npts <= 0) {
+		return 0;
+	}
+	SXS_CK(cudaSetDevice(device));
+	double *d_cross = NULL, *d_x = NULL, *d_a = NULL, *d_q = NULL, *d_res = NULL;
+	const size_t nx = (size_t)npts * 6 * qnum;
+	SXS_CK(cudaMalloc(&d_cross, sizeof(double) * nx));
+	SXS_CK(cudaMalloc(&d_x, sizeof(double) * nx));
+	SXS_CK(cudaMalloc(&d_a, sizeof(double) * 6 * qnum));
+	SXS_CK(cudaMalloc(&d_q, sizeof(double) * qnum));
+	SXS_CK(cudaMalloc(&d_res, sizeof(double) * 4 * npts));
+	SXS_CK(cudaMemcpy(d_cross, cross, sizeof(double) * nx, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_a, a, sizeof(double) * 6 * qnum, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_q, qvals, sizeof(double) * qnum, cudaMemcpyHostToDevice));
+	k_cross_to_strided<<<1184, 256>>>(d_cross, npts, qnum, d_x);
+	SXS_CK_LAUNCH();
+	int rc = sxs_launch_fit(d_x, npts, npts, d_a, d_q, qnum, mult, peak, rescale, d_res, 0);
+	if (rc == 0) {
+		SXS_CK(cudaMemcpy(out, d_res, sizeof(double) * 4 * npts, cudaMemcpyDeviceToHost));
+	}
+	cudaFree(d_cross); cudaFree(d_x); cudaFree(d_a); cudaFree(d_q); cudaFree(d_res);
+	return rc;
+}
+
+__global__ void k_fit_eval(const double *__restrict__ cross, const double *__restrict__ a,
+                           const double *__restrict__ qvals, int qnum, double mult, double c1, double c2,
+                           double *__restrict__ out4)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) {
+		return;
+	}
+	struct sxs_fit_ctx ctx;
+	ctx.x = cross; /* cross[k*qnum + q]: element (q,k) at (q*6+k)*stride needs a transposed view */
+	ctx.stride = 1;
+	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0;
+	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
+	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);
+}
+
+extern "C" int sxs_cuda_fit_eval(int device, const double *cross, const double *a, const double *qvals, int qnum,
+                                 double mult, double c1, double c2, double *out4)
+{
+	SXS_CK(cudaSetDevice(device));
+	/* host layout cross[k*qnum + q] -> device layout [(q*6 + k)] */
+	double *tmp = (double *)malloc(sizeof(double) * 6 * qnum);
+	for (int k = 0; k < 6; k++) {
+		for (int q = 0; q < qnum; q++) {
+			tmp[q * 6 + k] = cross[k * qnum + q];
+		}
+	}
+	double *d_x = NULL, *d_a = NULL, *d_q = NULL, *d_o = NULL;
+	SXS_CK(cudaMalloc(&d_x, sizeof(double) * 6 * qnum));
+	SXS_CK(cudaMalloc(&d_a, sizeof(double) * 6 * qnum));
+	SXS_CK(cudaMalloc(&d_q, sizeof(double) * qnum));
+	SXS_CK(cudaMalloc(&d_o, sizeof(double) * 4));
+	SXS_CK(cudaMemcpy(d_x, tmp, sizeof(double) * 6 * qnum, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_a, a, sizeof(double) * 6 * qnum, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_q, qvals, sizeof(double) * qnum, cudaMemcpyHostToDevice));
+	free(tmp);
+	k_fit_eval<<<1, 32>>>(d_x, d_a, d_q, qnum, mult, c1, c2, d_o);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaMemcpy(out4, d_o, sizeof(double) * 4, cudaMemcpyDeviceToHost));
+	cudaFree(d_x); cudaFree(d_a); cudaFree(d_q); cudaFree(d_o);
+	return 0;
+}
+
+/* ------------------------------------------------------------------ self terms */
+
+/* one thread per (k, q); serial over (l, m) in the reference's order */
+__global__ void k_pair_const(const double2 *__restrict__ A, const double2 *__restrict__ B, int qnum, int lm_n,
+                             double *__restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 6 * qnum) {
+		return;
+	}
+	const int k = i / qnum, q = i % qnum;
+	const int c1s[6] = {0, 0, 0, 1, 1, 2};
+	const int c2s[6] = {0, 1, 2, 1, 2, 2};
+	const double2 *A1 = A + ((size_t)c1s[k] * qnum + q) * lm_n, *A2 = A + ((size_t)c2s[k] * qnum + q) * lm_n;
+	const double2 *B1 = B + ((size_t)c1s[k] * qnum + q) * lm_n, *B2 = B + ((size_t)c2s[k] * qnum + q) * lm_n;
+	double in = 0.0;
+	for (int j = 0; j < lm_n; j++) {
+		in += A1[j].x * A2[j].x + A1[j].y * A2[j].y;
+		in += B1[j].x * B2[j].x + B1[j].y * B2[j].y;
+	}
+	out[i] = (c1s[k] != c2s[k]) ? in * 2.0 : in;
+}
+
+int sxs_launch_pair_const(const double *d_coefA, const double *d_coefB, int qnum, int L, double *d_out,
+                          cudaStream_t stream)
+{
+	const int n = 6 * qnum;
+	k_pair_const<<<(n + 127) / 128, 128, 0, stream>>>((const double2 *)d_coefA, (const double2 *)d_coefB, qnum,
+	                                                   (L + 1) * (L + 1), d_out);
+	SXS_CK_LAUNCH();
+	return 0;
+}
+
+__global__ void k_self_terms(const double2 *__restrict__ A, int qnum, int lm_n, double *__restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= 6 * qnum) {
+		return;
+	}
+	const int k = i / qnum, q = i % qnum;
+	const int c1s[6] = {0, 0, 0, 1, 1, 2};
+	const int c2s[6] = {0, 1, 2, 1, 2, 2};
+	const double2 *A1 = A + ((size_t)c1s[k] * qnum + q) * lm_n, *A2 = A + ((size_t)c2s[k] * qnum + q) * lm_n;
+	double acc = 0.0;
+	for (int j = 0; j < lm_n; j++) {
+		const double val = A1[j].x * A2[j].x + A1[j].y * A2[j].y;
+		acc += val;
+	}
+	out[i] = (c1s[k] != c2s[k]) ? acc * 2.0 : acc;
+}
+
+extern "C" int sxs_cuda_self_terms(int device, const double *coef, int qnum, int L, double *out)
+{
+	SXS_CK(cudaSetDevice(device));
+	const int lm_n = (L + 1) * (L + 1);
+	const size_t nc = (size_t)3 * qnum * lm_n * 2;
+	double *d_c = NULL, *d_o = NULL;
+	SXS_CK(cudaMalloc(&d_c, sizeof(double) * nc));
+	SXS_CK(cudaMalloc(&d_o, sizeof(double) * 6 * qnum));
+	SXS_CK(cudaMemcpy(d_c, coef, sizeof(double) * nc, cudaMemcpyHostToDevice));
+	k_self_terms<<<(6 * qnum + 127) / 128, 128>>>((const double2 *)d_c, qnum, lm_n, d_o);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaMemcpy(out, d_o, sizeof(double) * 6 * qnum, cudaMemcpyDeviceToHost));
+	cudaFree(d_c); cudaFree(d_o);
+	return 0;
+}
+
+/* I(q) = sum_lm |V - G D + c2 W|^2, G evaluated at qvals[0] for every q like the reference */
+__global__ void k_profile(const double2 *__restrict__ A, int qnum, int lm_n, double mult, double q0, double c1,
+                          double c2, double *__restrict__ in)
+{
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= qnum) {
+		return;
+	}
+	const double corr = -mult * (c1 * c1 - 1.0);
+	const double G = c1 * c1 * c1 * exp(corr * q0 * q0);
+	const double2 *V = A + ((size_t)0 * qnum + q) * lm_n, *D = A + ((size_t)1 * qnum + q) * lm_n,
+	              *W = A + ((size_t)2 * qnum + q) * lm_n;
+	double acc = 0.0;
+	for (int j = 0; j < lm_n; j++) {
+		const double a_re = V[j].x - G * D[j].x + c2 * W[j].x;
+		const double a_im = V[j].y - G * D[j].y + c2 * W[j].y;
+		acc += a_re * a_re + a_im * a_im;
+	}
+	in[q] = acc;
+}
+
+extern "C" int sxs_cuda_profile_from_spf(int device, const double *coef, int qnum, int L, double mult,
+                                         const double *qvals, double c1, double c2, double *intensity)
+{
+	SXS_CK(cudaSetDevice(device));
+	const int lm_n = (L + 1) * (L + 1);
+	const size_t nc = (size_t)3 * qnum * lm_n * 2;
+	double *d_c = NULL, *d_o = NULL;
+	SXS_CK(cudaMalloc(&d_c, sizeof(double) * nc));
+	SXS_CK(cudaMalloc(&d_o, sizeof(double) * qnum));
+	SXS_CK(cudaMemcpy(d_c, coef, sizeof(double) * nc, cudaMemcpyHostToDevice));
+	k_profile<<<(qnum + 63) / 64, 64>>>((const double2 *)d_c, qnum, lm_n, mult, qvals[0], c1, c2, d_o);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaMemcpy(intensity, d_o, sizeof(double) * qnum, cudaMemcpyDeviceToHost));
+	cudaFree(d_c); cudaFree(d_o);
+	return 0;
+}

@@ -1,0 +1,1045 @@
+/* K2-K4 orchestration: FFT-SAXS dimer scoring on one B200.
+ *
+ * Reference computation (src/fftsaxs.c:608-986), per z and per (beta1, beta2) cell:
+ *   sum1  S[q][m][m2][l]   = sum_l1 d^l1_{m m2}(b2) conj(B_{l1 m2} T^{|m|}_{l l1}(q z))          (:251-333)
+ *   sum2  G[m][m1][m2]     = sum_l  d^l_{m m1}(b1) A_{l m1} S[m][m2][l]   (6 component pairs)     (:416-524)
+ *   F[a2][g1][g2]          = Re 3-D DFT of G over (m, m1, m2)                                    (:529-606, fftw)
+ *   X_k[q]                 = const_k[q] + 2 F_k                                                 (:52-108)
+ *   fit (c1, c2) per listed grid point                                                          (:909)
+ *
+ * The DFT is separable and linear, so the two gamma transforms are applied to the coefficients
+ * BEFORE the l-contraction, once per molecule and independent of z:
+ *   At[b1][q][c][m,l][g1] = sum_m1 w^(m1 g1) d^l_{m m1}(b1)      A^c_{l m1}(q)        (k_rotate, receptor)
+ *   Bt[b2][q][c][m,l][g2] = sum_m2 w^(m2 g2) d^l_{m m2}(b2) conj(B^c_{l m2}(q))       (k_rotate, ligand)
+ *   St[z,b2][q][c][m,l][g2] = sum_l1 conj(T^m_{l l1}(q z)) Bt[b2][q][c][m,l1][g2]      (k_translate)
+ * and what is left per listed pose (z, b1, b2, a2, g1, g2) is the alpha transform of a length-(L+1) dot:
+ *   F_k = Re sum_m w^(m a2) sum_{l>=|m|} At^{c}[m,l,g1] St^{c'}[m,l,g2]                  (k_cross)
+ * Only m >= 0 is evaluated: the m <-> -m terms are complex conjugates of each other (A_{l,-m} =
+ * (-1)^{l+m} conj(A_{lm}) for real densities; verified to 6e-13 on the reference's golden inputs), so
+ * F = Re C_0 + 2 Re sum_{m>0}.  No N^3 grid is ever materialised; cost per pose is
+ * qnum * 9 * (L+1)(L+2)/2 complex MACs (0.49 MFLOP at L=15, Q=50) instead of N^3-sized transforms
+ * per cell.  w = exp(-2 pi i/N) comes from the host table built like the reference's direct DFT
+ * (truncated pi, src/fftsaxs.c:536-548).
+ *
+ * Pose list handling (replaces the O(cells*nout) mask scans, src/fftsaxs.c:716-733,850-872,922-936):
+ * keys (z,b2,b1,g1,g2,a2) are radix-sorted on the device, duplicates collapse into distinct grid
+ * points, each point is fitted once and scattered back to every row that named it.
+ */
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdarg.h>
+
+#include "sxs_dev.cuh"
+
+/* ------------------------------------------------------------------ errors */
+
+/* process-wide: the device threads of a multi-GPU call report through the thread that joins them */
+static char g_err[512] = "no error";
+
+extern "C" void sxs_cuda_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *sxs_cuda_last_error(void)
+{
+	return g_err;
+}
+
+extern "C" int sxs_cuda_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		return 0;
+	}
+	return n;
+}
+
+/* -------------------------------------------------------------------- plan */
+
+#define SXS_NTIMERS 5   /* 0 sort+points, 1 tmatrix+translate, 2 cross, 3 fit, 4 scatter */
+#define SXS_MAX_TIMED 256
+
+struct sxs_cuda_plan {
+	int device;
+	int L, nb, N, ML, qnum;
+	/* tables */
+	double *d_qvals, *d_dsymb, *d_dwig;
+	double2 *d_tw;
+	/* molecules */
+	double2 *d_coefA, *d_coefB;
+	double *d_const;  /* [6][qnum] */
+	double2 *d_At, *d_Bt; /* [beta][q][c][ml][g] */
+	int have_molecules;
+	/* experiment */
+	double *d_a;
+	double mult, peak;
+	int have_experiment;
+	/* translations */
+	double *d_bessel;
+	int znum;
+	/* workspace (grow-only) */
+	double2 *d_T;  size_t cap_T;   /* [zg][q][m][l][l1] */
+	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g] */
+	double *d_X;   size_t cap_X;   /* [q][6][chunk] */
+	double *d_res; size_t cap_res; /* [points][4] */
+	unsigned long long *d_keys, *d_keys_sorted, *d_pkeys;
+	unsigned int *d_rows, *d_rows_sorted, *d_pid;
+	size_t cap_rows;
+	void *d_cub; size_t cap_cub;
+	long long *d_zoff; int cap_zoff;
+	int *d_slab_flag; int cap_slab;
+	void *d_index_in; size_t cap_index_in;
+	double *d_out3; size_t cap_out3;
+	long long *h_zoff;
+	/* budgets */
+	size_t budget_St, budget_X;
+	long long stats[5];
+	/* optional per-kernel-class device timing (CUDA events on the launching stream) */
+	int profiling;
+	cudaEvent_t ev[SXS_NTIMERS][2 * SXS_MAX_TIMED];
+	int ev_used[SXS_NTIMERS];
+	double ms[SXS_NTIMERS];
+	long long timed_launches[SXS_NTIMERS];
+};
+
+static void timer_begin(sxs_cuda_plan *p, int which, cudaStream_t st)
+{
+	if (p->profiling && p->ev_used[which] < SXS_MAX_TIMED) {
+		cudaEventRecord(p->ev[which][2 * p->ev_used[which]], st);
+	}
+}
+
+static void timer_end(sxs_cuda_plan *p, int which, cudaStream_t st)
+{
+	if (p->profiling && p->ev_used[which] < SXS_MAX_TIMED) {
+		cudaEventRecord(p->ev[which][2 * p->ev_used[which] + 1], st);
+		p->ev_used[which]++;
+	}
+}
+
+/* Sums the recorded intervals (synchronises the last event of each class). */
+static void timer_collect(sxs_cuda_plan *p)
+{
+	for (int w = 0; w < SXS_NTIMERS; w++) {
+		p->ms[w] = 0.0;
+		p->timed_launches[w] = p->ev_used[w];
+		for (int i = 0; i < p->ev_used[w]; i++) {
+			float t = 0.f;
+			cudaEventSynchronize(p->ev[w][2 * i + 1]);
+			cudaEventElapsedTime(&t, p->ev[w][2 * i], p->ev[w][2 * i + 1]);
+			p->ms[w] += t;
+		}
+		p->ev_used[w] = 0;
+	}
+}
+
+template <typename T>
+static int ensure(T **ptr, size_t *cap, size_t need)
+{
+	if (need <= *cap && *ptr != NULL) {
+		return 0;
+	}
+	if (*ptr != NULL) {
+		cudaFree(*ptr);
+		*ptr = NULL;
+	}
+	size_t want = need + need / 8;
+	cudaError_t e = cudaMalloc((void **)ptr, want * sizeof(T));
+	if (e != cudaSuccess) {
+		want = need;
+		e = cudaMalloc((void **)ptr, want * sizeof(T));
+	}
+	if (e != cudaSuccess) {
+		*cap = 0;
+		sxs_cuda_set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+		return -1;
+	}
+	*cap = want;
+	return 0;
+}
+
+static size_t env_gb(const char *name, double dflt_gb)
+{
+	const char *v = getenv(name);
+	double gb = dflt_gb;
+	if (v != NULL && *v) {
+		gb = atof(v);
+	}
+	return (size_t)(gb * 1024.0 * 1024.0 * 1024.0);
+}
+
+extern "C" sxs_cuda_plan *sxs_cuda_plan_create(int device, int L, int qnum, const double *qvals, const double *dsymb,
+                                               const double *dwig, const double *twiddle)
+{
+	if (cudaSetDevice(device) != cudaSuccess) {
+		sxs_cuda_set_error("cudaSetDevice(%d) failed", device);
+		return NULL;
+	}
+	if (L < 1 || L > 127 || qnum < 1 || qnum > 512) {
+		sxs_cuda_set_error("unsupported L=%d or qnum=%d", L, qnum);
+		return NULL;
+	}
+	sxs_cuda_plan *p = (sxs_cuda_plan *)calloc(1, sizeof(*p));
+	p->device = device;
+	p->L = L; p->nb = L + 1; p->N = 2 * L + 1; p->ML = sxs_ml_count(L); p->qnum = qnum;
+	const size_t nds = (size_t)p->nb * p->nb * p->nb * p->N;
+	const size_t ndw = (size_t)p->nb * p->nb * p->N * p->N;
+	const size_t ncoef = (size_t)3 * qnum * p->nb * p->nb;
+	const size_t nrot = (size_t)p->nb * qnum * 3 * p->ML * p->N;
+	cudaError_t e = cudaSuccess;
+#define PC(call) do { if (e == cudaSuccess) e = (call); } while (0)
+	PC(cudaMalloc(&p->d_qvals, sizeof(double) * qnum));
+	PC(cudaMalloc(&p->d_dsymb, sizeof(double) * nds));
+	PC(cudaMalloc(&p->d_dwig, sizeof(double) * ndw));
+	PC(cudaMalloc(&p->d_tw, sizeof(double2) * p->N));
+	PC(cudaMalloc(&p->d_coefA, sizeof(double2) * ncoef));
+	PC(cudaMalloc(&p->d_coefB, sizeof(double2) * ncoef));
+	PC(cudaMalloc(&p->d_const, sizeof(double) * 6 * qnum));
+	PC(cudaMalloc(&p->d_At, sizeof(double2) * nrot));
+	PC(cudaMalloc(&p->d_Bt, sizeof(double2) * nrot));
+	PC(cudaMalloc(&p->d_a, sizeof(double) * 6 * qnum));
+	PC(cudaMemcpy(p->d_qvals, qvals, sizeof(double) * qnum, cudaMemcpyHostToDevice));
+	PC(cudaMemcpy(p->d_dsymb, dsymb, sizeof(double) * nds, cudaMemcpyHostToDevice));
+	PC(cudaMemcpy(p->d_dwig, dwig, sizeof(double) * ndw, cudaMemcpyHostToDevice));
+	PC(cudaMemcpy(p->d_tw, twiddle, sizeof(double2) * p->N, cudaMemcpyHostToDevice));
+	PC(cudaMallocHost(&p->h_zoff, sizeof(long long) * 4096));
+#undef PC
+	if (e != cudaSuccess) {
+		sxs_cuda_set_error("plan allocation failed: %s", cudaGetErrorString(e));
+		sxs_cuda_plan_destroy(p);
+		return NULL;
+	}
+	p->budget_St = env_gb("SXS_CUDA_ST_GB", 12.0);
+	p->budget_X = env_gb("SXS_CUDA_X_GB", 10.0);
+	return p;
+}
+
+extern "C" void sxs_cuda_plan_destroy(sxs_cuda_plan *p)
+{
+	if (p == NULL) {
+		return;
+	}
+	cudaSetDevice(p->device);
+	void *ptrs[] = {p->d_qvals, p->d_dsymb, p->d_dwig, p->d_tw, p->d_coefA, p->d_coefB, p->d_const, p->d_At, p->d_Bt,
+	                p->d_a, p->d_bessel, p->d_T, p->d_St, p->d_X, p->d_res, p->d_keys, p->d_keys_sorted, p->d_pkeys,
+	                p->d_rows, p->d_rows_sorted, p->d_pid, p->d_cub, p->d_zoff, p->d_slab_flag, p->d_index_in,
+	                p->d_out3};
+	for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
+		if (ptrs[i] != NULL) {
+			cudaFree(ptrs[i]);
+		}
+	}
+	if (p->h_zoff != NULL) {
+		cudaFreeHost(p->h_zoff);
+	}
+	free(p);
+}
+
+extern "C" int sxs_cuda_plan_stats(const sxs_cuda_plan *p, long long *stats5)
+{
+	memcpy(stats5, p->stats, sizeof(long long) * 5);
+	return 0;
+}
+
+extern "C" int sxs_cuda_plan_set_profiling(sxs_cuda_plan *p, int on)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	if (on && !p->profiling) {
+		for (int w = 0; w < SXS_NTIMERS; w++) {
+			for (int i = 0; i < 2 * SXS_MAX_TIMED; i++) {
+				SXS_CK(cudaEventCreate(&p->ev[w][i]));
+			}
+			p->ev_used[w] = 0;
+		}
+	}
+	p->profiling = on ? 1 : p->profiling; /* events stay allocated once created */
+	if (!on) {
+		for (int w = 0; w < SXS_NTIMERS; w++) p->ev_used[w] = 0;
+	}
+	return 0;
+}
+
+extern "C" int sxs_cuda_plan_kernel_times(sxs_cuda_plan *p, double *ms5, long long *launches5)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	timer_collect(p);
+	for (int w = 0; w < SXS_NTIMERS; w++) {
+		ms5[w] = p->ms[w];
+		launches5[w] = p->timed_launches[w];
+	}
+	return 0;
+}
+
+/* ------------------------------------------------ K2a: rotation + gamma DFT */
+
+/* out[b][q][c][ml][g] = sum_{m1=-l..l} w^(m1 g) d^l_{m m1}(beta_b) coef^c[q][l,m1]   (conj(coef) for the ligand).
+ * One thread per output element, g fastest: the d and coef operands are warp-uniform broadcasts. */
+__global__ void __launch_bounds__(256)
+k_rotate(int L, int qnum, const double *__restrict__ dwig, const double2 *__restrict__ coef,
+         const double2 *__restrict__ tw, int conjugate, double2 *__restrict__ out)
+{
+	extern __shared__ double2 s_tw[];
+	const int N = 2 * L + 1, nb = L + 1, ML = sxs_ml_count(L), lm_n = nb * nb;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) {
+		s_tw[i] = tw[i];
+	}
+	__syncthreads();
+	const size_t total = (size_t)nb * qnum * 3 * ML * N;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int g = (int)(e % N);
+		size_t rest = e / N;
+		const int ml = (int)(rest % ML); rest /= ML;
+		const int c = (int)(rest % 3); rest /= 3;
+		const int q = (int)(rest % qnum);
+		const int b = (int)(rest / qnum);
+		/* unpack ml -> (m, l): rows m hold l = m..L */
+		int m = 0, off = ml;
+		while (off >= nb - m) {
+			off -= nb - m;
+			m++;
+		}
+		const int l = m + off;
+		const double *drow = dwig + (((size_t)b * nb + l) * N + (m + L)) * N + L; /* index by m1 */
+		const double2 *crow = coef + ((size_t)c * qnum + q) * lm_n + l * (l + 1);   /* index by m1 */
+		double re = 0.0, im = 0.0;
+		int k = ((-l * g) % N + N) % N; /* (m1*g) mod N, advanced incrementally */
+		for (int m1 = -l; m1 <= l; m1++) {
+			const double d = drow[m1];
+			double2 a = crow[m1];
+			if (conjugate) {
+				a.y = -a.y;
+			}
+			const double2 w = s_tw[k];
+			const double pr = a.x * w.x - a.y * w.y;
+			const double pi = a.x * w.y + a.y * w.x;
+			re += d * pr;
+			im += d * pi;
+			k += g;
+			if (k >= N) {
+				k -= N;
+			}
+		}
+		out[e] = make_double2(re, im);
+	}
+}
+
+/* ------------------------------------------------------ K2b: translation */
+
+/* T^m_{l l1}(q z) = (-1)^m sum_p i^p dsymb[l,m,l1,p] j_p(q z), p = |l-l1| .. l+l1 ascending
+ * (fill_t_matrix, src/fftsaxs.c:182-243).  Layout T[((zl*qnum + q)*nb + m)*nb*nb + l*nb + l1]. */
+__global__ void __launch_bounds__(256)
+k_tmatrix(int L, int qnum, int nz, const int *__restrict__ zlist, const double *__restrict__ dsymb,
+          const double *__restrict__ bessel, double2 *__restrict__ T)
+{
+	const int nb = L + 1, N = 2 * L + 1;
+	const size_t per = (size_t)nb * nb * nb;
+	const size_t total = (size_t)nz * qnum * per;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int l1 = (int)(e % nb);
+		size_t rest = e / nb;
+		const int l = (int)(rest % nb); rest /= nb;
+		const int m = (int)(rest % nb); rest /= nb;
+		const int q = (int)(rest % qnum);
+		const int zl = (int)(rest / qnum);
+		if (l < m || l1 < l) {
+			continue; /* lower triangle is written by its mirror; l < m entries are never read */
+		}
+		const double sgn = (m % 2) ? -1.0 : 1.0;
+		const double *drow = dsymb + ((size_t)(l * (l + 1) + m) * nb + l1) * N;
+		const double *brow = bessel + ((size_t)zlist[zl] * qnum + q) * N;
+		double re = 0.0, im = 0.0;
+		for (int p = l1 - l; p <= l + l1; p++) {
+			const double val = __dmul_rn(__dmul_rn(sgn, drow[p]), brow[p]);
+			switch (p & 3) {
+			case 0: re = __dadd_rn(re, val); break;
+			case 1: im = __dadd_rn(im, val); break;
+			case 2: re = __dadd_rn(re, -val); break;
+			default: im = __dadd_rn(im, -val); break;
+			}
+		}
+		const size_t base = ((size_t)zl * qnum + q) * per + (size_t)m * nb * nb;
+		T[base + (size_t)l * nb + l1] = make_double2(re, im);
+		T[base + (size_t)l1 * nb + l] = make_double2(re, im);
+	}
+}
+
+/* St[slab][q][c][ml(m,l)][g] = sum_{l1=m..L} conj(T^m_{l l1}) Bt[b2][q][c][ml(m,l1)][g], slab = zl*nb + b2.
+ * Slabs whose (z, b2) holds no listed pose are skipped.  One thread per output element, g fastest. */
+__global__ void __launch_bounds__(256)
+k_translate(int L, int qnum, int nz, const int *__restrict__ slab_flag, const double2 *__restrict__ T,
+            const double2 *__restrict__ Bt, double2 *__restrict__ St)
+{
+	const int nb = L + 1, N = 2 * L + 1, ML = sxs_ml_count(L);
+	const size_t per_slab = (size_t)qnum * 3 * ML * N;
+	const size_t total = (size_t)nz * nb * per_slab;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int slab = (int)(e / per_slab);
+		if (!slab_flag[slab]) {
+			continue;
+		}
+		size_t rest = e % per_slab;
+		const int g = (int)(rest % N); rest /= N;
+		const int ml = (int)(rest % ML); rest /= ML;
+		const int c = (int)(rest % 3);
+		const int q = (int)(rest / 3);
+		const int zl = slab / nb, b2 = slab % nb;
+		int m = 0, off = ml;
+		while (off >= nb - m) {
+			off -= nb - m;
+			m++;
+		}
+		const int l = m + off;
+		const double2 *trow = T + (((size_t)zl * qnum + q) * nb + m) * nb * nb + (size_t)l * nb; /* index by l1 */
+		const double2 *brow = Bt + ((((size_t)b2 * qnum + q) * 3 + c) * ML + sxs_ml_index(L, m, m)) * N + g;
+		double re = 0.0, im = 0.0;
+		for (int l1 = m; l1 <= L; l1++) {
+			const double2 t = trow[l1];
+			const double2 b = brow[(size_t)(l1 - m) * N];
+			/* conj(t) * b */
+			re += t.x * b.x + t.y * b.y;
+			im += t.x * b.y - t.y * b.x;
+		}
+		St[e] = make_double2(re, im);
+	}
+}
+
+/* ----------------------------------------------------- pose list handling */
+
+#define SXS_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+/* flat index (z,b1,b2,a2,g1,g2 digits, src/index.c:9-29) -> sort key (z,b2,b1,g1,g2,a2) */
+template <typename IndexT>
+__global__ void k_make_keys(const IndexT *__restrict__ index, long long nout, int nb, int N, int z_lo, int z_hi,
+                            unsigned long long *__restrict__ keys, unsigned int *__restrict__ rows)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nout) {
+		return;
+	}
+	long long v = (long long)index[i];
+	unsigned long long key = SXS_KEY_NONE;
+	if (v >= 0) {
+		const long long g2 = v % N; v /= N;
+		const long long g1 = v % N; v /= N;
+		const long long a2 = v % N; v /= N;
+		const long long b2 = v % nb; v /= nb;
+		const long long b1 = v % nb;
+		const long long z = v / nb;
+		if (z >= z_lo && z < z_hi) {
+			key = (unsigned long long)((((((z * nb + b2) * nb + b1) * N + g1) * N + g2) * N) + a2);
+		}
+	}
+	keys[i] = key;
+	rows[i] = (unsigned int)i;
+}
+
+__global__ void k_mark_heads(const unsigned long long *__restrict__ ks, long long n, unsigned int *__restrict__ head)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	const unsigned long long k = ks[i];
+	head[i] = (k != SXS_KEY_NONE && (i == 0 || ks[i - 1] != k)) ? 1u : 0u;
+}
+
+/* pid_incl = inclusive scan of heads; point id of sorted row i is pid_incl[i]-1 */
+__global__ void k_compact_points(const unsigned long long *__restrict__ ks, const unsigned int *__restrict__ pid_incl,
+                                 long long n, unsigned long long *__restrict__ pkeys)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	const unsigned long long k = ks[i];
+	if (k != SXS_KEY_NONE && (i == 0 || ks[i - 1] != k)) {
+		pkeys[pid_incl[i] - 1] = k;
+	}
+}
+
+/* zoff[z] = first point whose z digit >= z (z = 0..znum); zoff[znum+1] = number of valid sorted rows */
+__global__ void k_z_offsets(const unsigned long long *__restrict__ pkeys, long long np,
+                            const unsigned long long *__restrict__ ks, long long n, int znum,
+                            unsigned long long per_z, long long *__restrict__ zoff)
+{
+	const int z = blockIdx.x * blockDim.x + threadIdx.x;
+	if (z <= znum) {
+		const unsigned long long target = (unsigned long long)z * per_z;
+		long long lo = 0, hi = np;
+		while (lo < hi) {
+			const long long mid = (lo + hi) >> 1;
+			if (pkeys[mid] < target) lo = mid + 1; else hi = mid;
+		}
+		zoff[z] = lo;
+	} else if (z == znum + 1) {
+		long long lo = 0, hi = n;
+		while (lo < hi) {
+			const long long mid = (lo + hi) >> 1;
+			if (ks[mid] != SXS_KEY_NONE) lo = mid + 1; else hi = mid;
+		}
+		zoff[z] = lo;
+	}
+}
+
+__global__ void k_slab_flags(const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0, int nb,
+                             unsigned long long per_zb2, int *__restrict__ flag)
+{
+	const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= p1) {
+		return;
+	}
+	const long long zb2 = (long long)(pkeys[p] / per_zb2); /* z*nb + b2 */
+	flag[zb2 - (long long)z0 * nb] = 1;
+}
+
+/* ------------------------------------------------------------ K3: cross terms */
+
+__device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double2 b)
+{
+	acc.x = fma(a.x, b.x, acc.x);
+	acc.x = fma(-a.y, b.y, acc.x);
+	acc.y = fma(a.x, b.y, acc.y);
+	acc.y = fma(a.y, b.x, acc.y);
+}
+
+/* One thread per distinct grid point, one q per blockIdx.y.  Consecutive threads are consecutive in
+ * (z, b2, b1, g1, g2, a2) order, so a block mostly works inside one cell: the receptor rows it reads
+ * differ only in g1 (nearly warp-uniform) and the ligand rows only in g2 — both 16-byte elements of the
+ * same 496-byte row, served by L1/L2.
+ * X[(q*6 + k)*xstride + (p - p0)] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108). */
+__global__ void __launch_bounds__(256)
+k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0,
+        const double2 *__restrict__ At, const double2 *__restrict__ St, const double2 *__restrict__ tw,
+        const double *__restrict__ cst, double *__restrict__ X, long long xstride)
+{
+	extern __shared__ double2 s_tw[];
+	const int N = 2 * L + 1, nb = L + 1, ML = sxs_ml_count(L);
+	for (int i = threadIdx.x; i < N; i += blockDim.x) {
+		s_tw[i] = tw[i];
+	}
+	__syncthreads();
+	const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= p1) {
+		return;
+	}
+	const int q = blockIdx.y;
+	unsigned long long key = pkeys[p];
+	const int a2 = (int)(key % N); key /= N;
+	const int g2 = (int)(key % N); key /= N;
+	const int g1 = (int)(key % N); key /= N;
+	const int b1 = (int)(key % nb); key /= nb;
+	const int b2 = (int)(key % nb);
+	const int z = (int)(key / nb);
+	const int slab = (z - z0) * nb + b2;
+
+	const size_t cstride = (size_t)ML * N;
+	const double2 *a_ptr = At + (((size_t)b1 * qnum + q) * 3) * cstride + g1;
+	const double2 *s_ptr = St + (((size_t)slab * qnum + q) * 3) * cstride + g2;
+
+	double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
+	int ka = 0; /* (m*a2) mod N */
+	size_t row = 0;
+	for (int m = 0; m <= L; m++) {
+		double2 cvv = {0, 0}, cvd = {0, 0}, cvw = {0, 0}, cdd = {0, 0}, cdw = {0, 0}, cww = {0, 0};
+		for (int l = m; l <= L; l++, row += N) {
+			const double2 av = __ldg(a_ptr + row), ad = __ldg(a_ptr + cstride + row), aw = __ldg(a_ptr + 2 * cstride + row);
+			const double2 sv = __ldg(s_ptr + row), sd = __ldg(s_ptr + cstride + row), sw = __ldg(s_ptr + 2 * cstride + row);
+			cmac(cvv, av, sv);
+			cmac(cvd, av, sd); cmac(cvd, ad, sv);
+			cmac(cvw, av, sw); cmac(cvw, aw, sv);
+			cmac(cdd, ad, sd);
+			cmac(cdw, ad, sw); cmac(cdw, aw, sd);
+			cmac(cww, aw, sw);
+		}
+		const double2 w = s_tw[ka];
+		const double fac = (m == 0) ? 1.0 : 2.0;
+		f0 += fac * (w.x * cvv.x - w.y * cvv.y);
+		f1 += fac * (w.x * cvd.x - w.y * cvd.y);
+		f2 += fac * (w.x * cvw.x - w.y * cvw.y);
+		f3 += fac * (w.x * cdd.x - w.y * cdd.y);
+		f4 += fac * (w.x * cdw.x - w.y * cdw.y);
+		f5 += fac * (w.x * cww.x - w.y * cww.y);
+		ka += a2;
+		if (ka >= N) {
+			ka -= N;
+		}
+	}
+	const long long col = p - p0;
+	double *xo = X + (size_t)q * 6 * xstride + col;
+	xo[0 * xstride] = cst[0 * qnum + q] + 2.0 * f0;
+	xo[1 * xstride] = cst[1 * qnum + q] + 2.0 * f1;
+	xo[2 * xstride] = cst[2 * qnum + q] + 2.0 * f2;
+	xo[3 * xstride] = cst[3 * qnum + q] + 2.0 * f3;
+	xo[4 * xstride] = cst[4 * qnum + q] + 2.0 * f4;
+	xo[5 * xstride] = cst[5 * qnum + q] + 2.0 * f5;
+}
+
+/* ---------------------------------------------------------------- scatter */
+
+/* sorted row i (valid rows only) -> point pid_incl[i]-1 -> user arrays at rows_sorted[i] */
+__global__ void k_scatter(const unsigned int *__restrict__ rows_sorted, const unsigned int *__restrict__ pid_incl,
+                          long long nvalid, const double *__restrict__ res, double *__restrict__ scores,
+                          double *__restrict__ c1, double *__restrict__ c2)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nvalid) {
+		return;
+	}
+	const unsigned int row = rows_sorted[i];
+	const double *r = res + (size_t)(pid_incl[i] - 1) * 4;
+	scores[row] = r[0];
+	c1[row] = r[1];
+	c2[row] = r[2];
+}
+
+/* compact variant for the host path: out3[i*3..] in sorted order, row ids come from rows_sorted */
+__global__ void k_gather_sorted(const unsigned int *__restrict__ pid_incl, long long nvalid,
+                                const double *__restrict__ res, double *__restrict__ out3)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nvalid) {
+		return;
+	}
+	const double *r = res + (size_t)(pid_incl[i] - 1) * 4;
+	out3[i * 3 + 0] = r[0];
+	out3[i * 3 + 1] = r[1];
+	out3[i * 3 + 2] = r[2];
+}
+
+/* cross terms of sorted rows back to list order (stage access for the parity tests) */
+__global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, const unsigned int *__restrict__ pid_incl,
+                               long long nvalid, long long p0, long long p1, const double *__restrict__ X,
+                               long long xstride, int qnum, double *__restrict__ cross)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nvalid) {
+		return;
+	}
+	const long long p = (long long)pid_incl[i] - 1;
+	if (p < p0 || p >= p1) {
+		return;
+	}
+	const unsigned int row = rows_sorted[i];
+	for (int q = 0; q < qnum; q++) {
+		for (int k = 0; k < 6; k++) {
+			cross[((size_t)row * 6 + k) * qnum + q] = X[((size_t)q * 6 + k) * xstride + (p - p0)];
+		}
+	}
+}
+
+/* ------------------------------------------------------------ plan set-up */
+
+static unsigned grid_for(size_t total, int threads, unsigned cap = 148u * 16u)
+{
+	size_t b = (total + threads - 1) / threads;
+	if (b > cap) b = cap;
+	if (b < 1) b = 1;
+	return (unsigned)b;
+}
+
+extern "C" int sxs_cuda_plan_set_molecules(sxs_cuda_plan *p, const double *coefA, const double *coefB)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	const size_t ncoef = (size_t)3 * p->qnum * p->nb * p->nb;
+	SXS_CK(cudaMemcpy(p->d_coefA, coefA, sizeof(double2) * ncoef, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(p->d_coefB, coefB, sizeof(double2) * ncoef, cudaMemcpyHostToDevice));
+	if (sxs_launch_pair_const((const double *)p->d_coefA, (const double *)p->d_coefB, p->qnum, p->L, p->d_const, 0) != 0) {
+		return -1;
+	}
+	const size_t nrot = (size_t)p->nb * p->qnum * 3 * p->ML * p->N;
+	const size_t shm = sizeof(double2) * p->N;
+	k_rotate<<<grid_for(nrot, 256), 256, shm>>>(p->L, p->qnum, p->d_dwig, p->d_coefA, p->d_tw, 0, p->d_At);
+	SXS_CK_LAUNCH();
+	k_rotate<<<grid_for(nrot, 256), 256, shm>>>(p->L, p->qnum, p->d_dwig, p->d_coefB, p->d_tw, 1, p->d_Bt);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaDeviceSynchronize());
+	p->have_molecules = 1;
+	return 0;
+}
+
+extern "C" int sxs_cuda_plan_set_experiment(sxs_cuda_plan *p, const double *a, double mult, double peak)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	SXS_CK(cudaMemcpy(p->d_a, a, sizeof(double) * 6 * p->qnum, cudaMemcpyHostToDevice));
+	p->mult = mult;
+	p->peak = peak;
+	p->have_experiment = 1;
+	return 0;
+}
+
+extern "C" int sxs_cuda_plan_set_translations(sxs_cuda_plan *p, const double *bessel, int znum)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	if (znum < 1 || znum > 4000) {
+		sxs_cuda_set_error("znum %d out of range", znum);
+		return -1;
+	}
+	if (p->d_bessel != NULL) {
+		cudaFree(p->d_bessel);
+		p->d_bessel = NULL;
+	}
+	const size_t n = (size_t)znum * p->qnum * p->N;
+	SXS_CK(cudaMalloc(&p->d_bessel, sizeof(double) * n));
+	SXS_CK(cudaMemcpy(p->d_bessel, bessel, sizeof(double) * n, cudaMemcpyHostToDevice));
+	p->znum = znum;
+	return 0;
+}
+
+/* ------------------------------------------------------------ score (core) */
+
+template <typename IndexT>
+static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, int z_lo, int z_hi, double *d_scores,
+                      double *d_c1, double *d_c2, double *d_out3_sorted, double *d_cross_out, cudaStream_t st,
+                      long long *nvalid_out)
+{
+	if (!p->have_molecules || !p->have_experiment || p->d_bessel == NULL) {
+		sxs_cuda_set_error("plan is missing molecules, experiment or translations");
+		return -1;
+	}
+	if (nout > 0x7FFFFFF0ll) {
+		sxs_cuda_set_error("more than 2^31 rows per call");
+		return -1;
+	}
+	memset(p->stats, 0, sizeof(p->stats));
+	if (nvalid_out) *nvalid_out = 0;
+	if (nout <= 0) {
+		return 0;
+	}
+	if (z_lo < 0) z_lo = 0;
+	if (z_hi > p->znum) z_hi = p->znum;
+	if (z_hi <= z_lo) {
+		return 0;
+	}
+	const int L = p->L, nb = p->nb, N = p->N, ML = p->ML, Q = p->qnum, znum = p->znum;
+	long long launches = 0;
+
+	/* --- keys, sort, distinct points --- */
+	size_t cap;
+	cap = p->cap_rows;
+	if ((size_t)nout > p->cap_rows || p->d_keys == NULL) {
+		size_t c1_ = 0, c2_ = 0, c3_ = 0, c4_ = 0, c5_ = 0, c6_ = 0;
+		void *olds[] = {p->d_keys, p->d_keys_sorted, p->d_pkeys, p->d_rows, p->d_rows_sorted, p->d_pid};
+		for (int i = 0; i < 6; i++) if (olds[i]) cudaFree(olds[i]);
+		p->d_keys = p->d_keys_sorted = p->d_pkeys = NULL;
+		p->d_rows = p->d_rows_sorted = p->d_pid = NULL;
+		if (ensure(&p->d_keys, &c1_, (size_t)nout) || ensure(&p->d_keys_sorted, &c2_, (size_t)nout) ||
+		    ensure(&p->d_pkeys, &c3_, (size_t)nout) || ensure(&p->d_rows, &c4_, (size_t)nout) ||
+		    ensure(&p->d_rows_sorted, &c5_, (size_t)nout) || ensure(&p->d_pid, &c6_, (size_t)nout)) {
+			p->cap_rows = 0;
+			return -1;
+		}
+		p->cap_rows = (size_t)nout;
+	}
+	(void)cap;
+	const int T256 = 256;
+	const unsigned gb = (unsigned)((nout + T256 - 1) / T256);
+	timer_begin(p, 0, st);
+	k_make_keys<IndexT><<<gb, T256, 0, st>>>(d_index, nout, nb, N, z_lo, z_hi, p->d_keys, p->d_rows);
+	SXS_CK_LAUNCH(); launches++;
+
+	unsigned long long max_key = ((unsigned long long)znum * nb * nb) * (unsigned long long)N * N * N;
+	int bits = 1;
+	while (bits < 64 && (max_key >> bits) != 0) bits++;
+	/* the sentinel has every bit set: sorting on all 64 bits keeps it last */
+	(void)bits;
+	size_t need = 0, need2 = 0;
+	cub::DeviceRadixSort::SortPairs(NULL, need, p->d_keys, p->d_keys_sorted, p->d_rows, p->d_rows_sorted, (int)nout, 0, 64, st);
+	cub::DeviceScan::InclusiveSum(NULL, need2, p->d_pid, p->d_pid, (int)nout, st);
+	if (need2 > need) need = need2;
+	{
+		unsigned char *tmp = (unsigned char *)p->d_cub;
+		size_t c = p->cap_cub;
+		if (ensure(&tmp, &c, need + 256)) return -1;
+		p->d_cub = tmp; p->cap_cub = c;
+	}
+	size_t tb = p->cap_cub;
+	cub::DeviceRadixSort::SortPairs(p->d_cub, tb, p->d_keys, p->d_keys_sorted, p->d_rows, p->d_rows_sorted, (int)nout, 0, 64, st);
+	/* heads -> inclusive scan (reuse d_rows as the head buffer: the unsorted row ids are no longer needed) */
+	k_mark_heads<<<gb, T256, 0, st>>>(p->d_keys_sorted, nout, p->d_rows);
+	SXS_CK_LAUNCH(); launches++;
+	tb = p->cap_cub;
+	cub::DeviceScan::InclusiveSum(p->d_cub, tb, p->d_rows, p->d_pid, (int)nout, st);
+	k_compact_points<<<gb, T256, 0, st>>>(p->d_keys_sorted, p->d_pid, nout, p->d_pkeys);
+	SXS_CK_LAUNCH(); launches++;
+	timer_end(p, 0, st);
+
+	/* number of points: last inclusive-scan value (read back together with the z offsets) */
+	if (p->d_zoff == NULL || p->cap_zoff < znum + 4) {
+		if (p->d_zoff) cudaFree(p->d_zoff);
+		SXS_CK(cudaMalloc(&p->d_zoff, sizeof(long long) * (znum + 4)));
+		p->cap_zoff = znum + 4;
+	}
+	if (znum + 4 > 4096) {
+		sxs_cuda_set_error("znum too large for the offset buffer");
+		return -1;
+	}
+	/* np is needed by the binary search: read it first (tiny sync) */
+	unsigned int np_u = 0;
+	SXS_CK(cudaMemcpyAsync(&np_u, p->d_pid + (nout - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+	SXS_CK(cudaStreamSynchronize(st));
+	const long long np = (long long)np_u;
+	if (np == 0) {
+		return 0;
+	}
+	const unsigned long long per_zb2 = (unsigned long long)nb * N * N * N;
+	const unsigned long long per_z = per_zb2 * nb;
+	k_z_offsets<<<(znum + 2 + 127) / 128, 128, 0, st>>>(p->d_pkeys, np, p->d_keys_sorted, nout, znum, per_z, p->d_zoff);
+	SXS_CK_LAUNCH(); launches++;
+	SXS_CK(cudaMemcpyAsync(p->h_zoff, p->d_zoff, sizeof(long long) * (znum + 2), cudaMemcpyDeviceToHost, st));
+	SXS_CK(cudaStreamSynchronize(st));
+	const long long *zoff = p->h_zoff;
+	const long long nvalid = zoff[znum + 1];
+	if (nvalid_out) *nvalid_out = nvalid;
+
+	/* --- result buffer for all points --- */
+	if (ensure(&p->d_res, &p->cap_res, (size_t)np * 4)) return -1;
+
+	/* --- group sizing --- */
+	const size_t slab_elems = (size_t)Q * 3 * ML * N;           /* double2 per (z,b2) slab */
+	const size_t per_z_bytes = slab_elems * nb * sizeof(double2);
+	int zg_max = (int)(p->budget_St / per_z_bytes);
+	if (zg_max < 1) zg_max = 1;
+	if (zg_max > z_hi - z_lo) zg_max = z_hi - z_lo;
+	long long chunk_max = (long long)(p->budget_X / (sizeof(double) * 6 * Q));
+	if (chunk_max < 1024) chunk_max = 1024;
+	if (chunk_max > np) chunk_max = np;
+	/* never size past what this call needs */
+	{
+		int zused = 0;
+		for (int z = z_lo; z < z_hi; z++) zused += (zoff[z + 1] > zoff[z]);
+		if (zg_max > zused) zg_max = zused > 0 ? zused : 1;
+	}
+	if (ensure(&p->d_St, &p->cap_St, slab_elems * nb * (size_t)zg_max)) return -1;
+	if (ensure(&p->d_T, &p->cap_T, (size_t)zg_max * Q * nb * nb * nb)) return -1;
+	if (ensure(&p->d_X, &p->cap_X, (size_t)chunk_max * 6 * Q)) return -1;
+	if (p->d_slab_flag == NULL || p->cap_slab < zg_max * nb + zg_max) {
+		if (p->d_slab_flag) cudaFree(p->d_slab_flag);
+		SXS_CK(cudaMalloc(&p->d_slab_flag, sizeof(int) * (zg_max * nb + zg_max)));
+		p->cap_slab = zg_max * nb + zg_max;
+	}
+	int *d_zlist = p->d_slab_flag + zg_max * nb;
+	int *h_zlist = (int *)malloc(sizeof(int) * zg_max);
+
+	long long nslabs_total = 0, ngroups = 0;
+	int z = z_lo;
+	while (z < z_hi) {
+		/* gather up to zg_max z steps that hold points; they need not be contiguous, only ordered */
+		int nz = 0;
+		int z_first = -1, z_last = -1;
+		while (z < z_hi && nz < zg_max) {
+			if (zoff[z + 1] > zoff[z]) {
+				if (z_first < 0) z_first = z;
+				z_last = z;
+				nz++;
+			}
+			z++;
+			if (z_first >= 0 && (z - z_first) >= zg_max) break; /* slabs are addressed by z - z_first */
+		}
+		if (nz == 0) break;
+		const int zspan = z_last - z_first + 1;
+		for (int i = 0; i < zspan; i++) h_zlist[i] = z_first + i;
+		const long long g0 = zoff[z_first], g1 = zoff[z_last + 1];
+		ngroups++;
+
+		SXS_CK(cudaMemsetAsync(p->d_slab_flag, 0, sizeof(int) * zspan * nb, st));
+		SXS_CK(cudaMemcpyAsync(d_zlist, h_zlist, sizeof(int) * zspan, cudaMemcpyHostToDevice, st));
+		timer_begin(p, 1, st);
+		k_slab_flags<<<(unsigned)((g1 - g0 + 255) / 256), 256, 0, st>>>(p->d_pkeys, g0, g1, z_first, nb, per_zb2, p->d_slab_flag);
+		SXS_CK_LAUNCH(); launches++;
+		k_tmatrix<<<grid_for((size_t)zspan * Q * nb * nb * nb, 256), 256, 0, st>>>(L, Q, zspan, d_zlist, p->d_dsymb, p->d_bessel, p->d_T);
+		SXS_CK_LAUNCH(); launches++;
+		k_translate<<<grid_for(slab_elems * nb * zspan, 256, 148u * 64u), 256, 0, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		SXS_CK_LAUNCH(); launches++;
+		timer_end(p, 1, st);
+		nslabs_total += (long long)zspan * nb;
+
+		for (long long c0 = g0; c0 < g1; c0 += chunk_max) {
+			const long long c1e = (c0 + chunk_max < g1) ? c0 + chunk_max : g1;
+			const long long cnt = c1e - c0;
+			dim3 grid((unsigned)((cnt + 255) / 256), Q);
+			timer_begin(p, 2, st);
+			k_cross<<<grid, 256, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, z_first, p->d_At, p->d_St, p->d_tw,
+			                                                 p->d_const, p->d_X, cnt);
+			SXS_CK_LAUNCH(); launches++;
+			timer_end(p, 2, st);
+			if (d_cross_out != NULL) {
+				k_gather_cross<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_rows_sorted, p->d_pid, nvalid, c0, c1e,
+				                                                              p->d_X, cnt, Q, d_cross_out);
+				SXS_CK_LAUNCH(); launches++;
+			}
+			timer_begin(p, 3, st);
+			if (sxs_launch_fit(p->d_X, cnt, cnt, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)c0 * 4, st) != 0) {
+				free(h_zlist);
+				return -1;
+			}
+			launches++;
+			timer_end(p, 3, st);
+		}
+	}
+	free(h_zlist);
+
+	timer_begin(p, 4, st);
+	if (d_scores != NULL) {
+		k_scatter<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_rows_sorted, p->d_pid, nvalid, p->d_res, d_scores, d_c1, d_c2);
+		SXS_CK_LAUNCH(); launches++;
+	}
+	if (d_out3_sorted != NULL) {
+		k_gather_sorted<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_pid, nvalid, p->d_res, d_out3_sorted);
+		SXS_CK_LAUNCH(); launches++;
+	}
+	timer_end(p, 4, st);
+	p->stats[0] = np;
+	p->stats[1] = nslabs_total;
+	p->stats[2] = launches;
+	p->stats[4] = ngroups;
+	return 0;
+}
+
+/* ----------------------------------------------------------- public score */
+
+extern "C" int sxs_cuda_plan_score_dev_i32(sxs_cuda_plan *p, const int *d_index, long long nout, int z_lo, int z_hi,
+                                           double *d_scores, double *d_c1, double *d_c2, void *stream)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	return score_core<int>(p, d_index, nout, z_lo, z_hi, d_scores, d_c1, d_c2, NULL, NULL, (cudaStream_t)stream, NULL);
+}
+
+extern "C" int sxs_cuda_plan_score_dev_i64(sxs_cuda_plan *p, const long long *d_index, long long nout, int z_lo,
+                                           int z_hi, double *d_scores, double *d_c1, double *d_c2, void *stream)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	return score_core<long long>(p, d_index, nout, z_lo, z_hi, d_scores, d_c1, d_c2, NULL, NULL, (cudaStream_t)stream, NULL);
+}
+
+template <typename IndexT>
+static int score_host(sxs_cuda_plan *p, const IndexT *index, long long nout, int z_lo, int z_hi, double *scores,
+                      double *c1, double *c2)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	if (nout <= 0) {
+		return 0;
+	}
+	{
+		unsigned char *tmp = (unsigned char *)p->d_index_in;
+		size_t c = p->cap_index_in;
+		if (ensure(&tmp, &c, sizeof(IndexT) * (size_t)nout)) return -1;
+		p->d_index_in = tmp; p->cap_index_in = c;
+	}
+	if (ensure(&p->d_out3, &p->cap_out3, (size_t)nout * 3)) return -1;
+	SXS_CK(cudaMemcpy(p->d_index_in, index, sizeof(IndexT) * (size_t)nout, cudaMemcpyHostToDevice));
+	long long nvalid = 0;
+	if (score_core<IndexT>(p, (const IndexT *)p->d_index_in, nout, z_lo, z_hi, NULL, NULL, NULL, p->d_out3, NULL, 0, &nvalid) != 0) {
+		return -1;
+	}
+	SXS_CK(cudaDeviceSynchronize());
+	if (nvalid == 0) {
+		return 0;
+	}
+	double *h3 = (double *)malloc(sizeof(double) * 3 * (size_t)nvalid);
+	unsigned int *hrows = (unsigned int *)malloc(sizeof(unsigned int) * (size_t)nvalid);
+	if (h3 == NULL || hrows == NULL) {
+		sxs_cuda_set_error("host allocation failed");
+		free(h3); free(hrows);
+		return -1;
+	}
+	SXS_CK(cudaMemcpy(h3, p->d_out3, sizeof(double) * 3 * (size_t)nvalid, cudaMemcpyDeviceToHost));
+	SXS_CK(cudaMemcpy(hrows, p->d_rows_sorted, sizeof(unsigned int) * (size_t)nvalid, cudaMemcpyDeviceToHost));
+	for (long long i = 0; i < nvalid; i++) {
+		const unsigned int r = hrows[i];
+		scores[r] = h3[3 * i];
+		c1[r] = h3[3 * i + 1];
+		c2[r] = h3[3 * i + 2];
+	}
+	free(h3);
+	free(hrows);
+	return 0;
+}
+
+extern "C" int sxs_cuda_plan_score_i32(sxs_cuda_plan *p, const int *index, long long nout, int z_lo, int z_hi,
+                                       double *scores, double *c1, double *c2)
+{
+	return score_host<int>(p, index, nout, z_lo, z_hi, scores, c1, c2);
+}
+
+extern "C" int sxs_cuda_plan_score_i64(sxs_cuda_plan *p, const long long *index, long long nout, int z_lo, int z_hi,
+                                       double *scores, double *c1, double *c2)
+{
+	return score_host<long long>(p, index, nout, z_lo, z_hi, scores, c1, c2);
+}
+
+extern "C" int sxs_cuda_plan_cross_terms_i32(sxs_cuda_plan *p, const int *index, long long nout, double *cross)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	if (nout <= 0) {
+		return 0;
+	}
+	int *d_idx = NULL;
+	double *d_cross = NULL;
+	const size_t nc = (size_t)nout * 6 * p->qnum;
+	SXS_CK(cudaMalloc(&d_idx, sizeof(int) * (size_t)nout));
+	SXS_CK(cudaMalloc(&d_cross, sizeof(double) * nc));
+	SXS_CK(cudaMemset(d_cross, 0, sizeof(double) * nc));
+	SXS_CK(cudaMemcpy(d_idx, index, sizeof(int) * (size_t)nout, cudaMemcpyHostToDevice));
+	int rc = score_core<int>(p, d_idx, nout, 0, p->znum, NULL, NULL, NULL, NULL, d_cross, 0, NULL);
+	if (rc == 0) {
+		SXS_CK(cudaDeviceSynchronize());
+		SXS_CK(cudaMemcpy(cross, d_cross, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+	}
+	cudaFree(d_idx);
+	cudaFree(d_cross);
+	return rc;
+}
+
+/* ------------------------------------------------------------ calibration */
+
+/* FP64 FMA rate of this GPU: 8 independent DFMA chains per thread, full occupancy.  MEASURED_PEAKS.json
+ * carries no FP64 figure, so bench.py calibrates the roofline denominator of K3/K4 with this. */
+__global__ void __launch_bounds__(256)
+k_dfma_peak(double *out, int iters, double seed)
+{
+	double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+	const double b = 1.0000001, c = 1e-9;
+#pragma unroll 1
+	for (int i = 0; i < iters; i++) {
+#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+			a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+		}
+	}
+	out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int sxs_cuda_fp64_peak(int device, double *tflops)
+{
+	SXS_CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	SXS_CK(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+	double *d = NULL;
+	SXS_CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+	cudaEvent_t e0, e1;
+	SXS_CK(cudaEventCreate(&e0));
+	SXS_CK(cudaEventCreate(&e1));
+	double best = 0.0;
+	for (int rep = 0; rep < 5; rep++) {
+		SXS_CK(cudaEventRecord(e0));
+		k_dfma_peak<<<blocks, threads>>>(d, iters, 1.0 + rep);
+		SXS_CK(cudaEventRecord(e1));
+		SXS_CK(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		SXS_CK(cudaEventElapsedTime(&ms, e0, e1));
+		const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+		const double tf = fl / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tflops = best;
+	return 0;
+}

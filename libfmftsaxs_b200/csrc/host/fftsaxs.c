@@ -1,0 +1,230 @@
+/* sxs_compute_saxs_scores: host orchestration of the GPU scoring pipeline.
+ *
+ * Work split (reference: src/fftsaxs.c:608-986, single-threaded, optional MPI over z in the caller):
+ *   host, once per L  : 3j d-symbols, Wigner-d on the beta grid, DFT phases (tables.c, cached)
+ *   host, per call    : j_p(q z) table with the reference-exact series (tiny: znum*qnum*(2L+1))
+ *   GPU               : everything else — rotated coefficient tables, z-translation, cross terms of every
+ *                       listed grid point, the (c1,c2) fit, scatter back to list order.
+ * z-steps are sharded over the CUDA devices named by SXS_CUDA_DEVICES (default all), one host thread
+ * per device, in place of the reference's MPI decomposition (tools/correlate.c:140-147); each device
+ * writes only the rows of its own z range, so no reduction is needed.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+
+#include "fftsaxs.h"
+#include "sxs_host.h"
+#include "sxs_tables.h"
+
+int sxs_host_device_list(int *devices, int cap)
+{
+	const int visible = sxs_cuda_device_count();
+	int n = 0;
+	const char *env = getenv("SXS_CUDA_DEVICES");
+	if (env != NULL && *env) {
+		const char *p = env;
+		while (*p && n < cap) {
+			char *end;
+			long v = strtol(p, &end, 10);
+			if (end == p) {
+				break;
+			}
+			if (v >= 0 && v < visible) {
+				devices[n++] = (int)v;
+			}
+			p = (*end == ',') ? end + 1 : end;
+		}
+	} else {
+		for (int d = 0; d < visible && n < cap; d++) {
+			devices[n++] = d;
+		}
+	}
+	if (n == 0) {
+		ERROR_MSG("no usable CUDA device: this library has no CPU path");
+	}
+	return n;
+}
+
+int sxs_host_default_device(void)
+{
+	int dev[64];
+	sxs_host_device_list(dev, 64);
+	return dev[0];
+}
+
+/* One cached plan per device; rebuilt when (L, q grid) changes. */
+#define SXS_MAX_DEV 64
+static struct {
+	sxs_cuda_plan *plan;
+	int L, qnum;
+	double *qvals;
+} g_plans[SXS_MAX_DEV];
+
+static sxs_cuda_plan *plan_for(int device, int L, int qnum, const double *qvals, const struct sxs_l_tables *t)
+{
+	if (device < 0 || device >= SXS_MAX_DEV) {
+		ERROR_MSG("device id out of range");
+	}
+	if (g_plans[device].plan != NULL && g_plans[device].L == L && g_plans[device].qnum == qnum &&
+	    !memcmp(g_plans[device].qvals, qvals, sizeof(double) * qnum)) {
+		return g_plans[device].plan;
+	}
+	if (g_plans[device].plan != NULL) {
+		sxs_cuda_plan_destroy(g_plans[device].plan);
+		free(g_plans[device].qvals);
+		g_plans[device].plan = NULL;
+	}
+	sxs_cuda_plan *p = sxs_cuda_plan_create(device, L, qnum, qvals, t->dsymb, t->dwig, t->twiddle);
+	if (p == NULL) {
+		fprintf(stderr, "[Error] sxs_cuda_plan_create: %s\n", sxs_cuda_last_error());
+		exit(EXIT_FAILURE);
+	}
+	g_plans[device].plan = p;
+	g_plans[device].L = L;
+	g_plans[device].qnum = qnum;
+	g_plans[device].qvals = (double *)malloc(sizeof(double) * qnum);
+	memcpy(g_plans[device].qvals, qvals, sizeof(double) * qnum);
+	return p;
+}
+
+struct shard_job {
+	sxs_cuda_plan *plan;
+	const double *coefA, *coefB, *a, *bessel;
+	double mult, peak;
+	int znum, z_lo, z_hi;
+	const int *idx32;
+	const long long *idx64;
+	long long nout;
+	double *scores, *c1, *c2;
+	int rc;
+};
+
+static void *shard_main(void *arg)
+{
+	struct shard_job *j = (struct shard_job *)arg;
+	j->rc = sxs_cuda_plan_set_molecules(j->plan, j->coefA, j->coefB);
+	if (j->rc == 0) j->rc = sxs_cuda_plan_set_experiment(j->plan, j->a, j->mult, j->peak);
+	if (j->rc == 0) j->rc = sxs_cuda_plan_set_translations(j->plan, j->bessel, j->znum);
+	if (j->rc == 0) {
+		if (j->idx32 != NULL) {
+			j->rc = sxs_cuda_plan_score_i32(j->plan, j->idx32, j->nout, j->z_lo, j->z_hi, j->scores, j->c1, j->c2);
+		} else {
+			j->rc = sxs_cuda_plan_score_i64(j->plan, j->idx64, j->nout, j->z_lo, j->z_hi, j->scores, j->c1, j->c2);
+		}
+	}
+	return NULL;
+}
+
+static void score_impl(double *scores, double *c1, double *c2, const int *idx32, const long long *idx64,
+                       long long nout, struct sxs_spf_full *A, struct sxs_spf_full *B, struct sxs_opt_params *params,
+                       double *qvals, int qnum, double *zvals, int znum, int L)
+{
+	CHECK_PTR(A);
+	CHECK_PTR(B);
+	CHECK_PTR(params);
+	if (nout <= 0 || znum <= 0) {
+		return;
+	}
+	const struct sxs_l_tables *t = sxs_l_tables_get(L);
+	const int N = 2 * L + 1, nb = L + 1;
+
+	const size_t ncoef = (size_t)3 * qnum * nb * nb * 2;
+	double *coefA = (double *)malloc(sizeof(double) * ncoef);
+	double *coefB = (double *)malloc(sizeof(double) * ncoef);
+	double *bessel = (double *)malloc(sizeof(double) * (size_t)znum * qnum * N);
+	CHECK_PTR(coefA); CHECK_PTR(coefB); CHECK_PTR(bessel);
+	sxs_spf_full_pack(A, coefA);
+	sxs_spf_full_pack(B, coefB);
+	sxs_fill_bessel_table(bessel, zvals, znum, qvals, qnum, L);
+
+	/* rows per z digit -> contiguous z ranges of roughly equal row count, one per device */
+	int dev[SXS_MAX_DEV];
+	int ndev = sxs_host_device_list(dev, SXS_MAX_DEV);
+	long long *per_z = (long long *)calloc((size_t)znum, sizeof(long long));
+	CHECK_PTR(per_z);
+	const long long cell5 = (long long)nb * nb * N * N * N;
+	long long total = 0;
+	for (long long i = 0; i < nout; i++) {
+		long long v = idx32 != NULL ? (long long)idx32[i] : idx64[i];
+		if (v >= 0 && v / cell5 < znum) {
+			per_z[v / cell5]++;
+			total++;
+		}
+	}
+	int nz_used = 0;
+	for (int z = 0; z < znum; z++) {
+		nz_used += per_z[z] > 0;
+	}
+	if (ndev > nz_used) {
+		ndev = nz_used > 0 ? nz_used : 1;
+	}
+
+	struct shard_job jobs[SXS_MAX_DEV];
+	pthread_t threads[SXS_MAX_DEV];
+	int z_next = 0;
+	long long done = 0;
+	int njobs = 0;
+	for (int d = 0; d < ndev; d++) {
+		long long want = (total * (d + 1)) / ndev;
+		int z_lo = z_next;
+		while (z_next < znum && (done < want || d == ndev - 1)) {
+			done += per_z[z_next++];
+			if (d < ndev - 1 && done >= want) {
+				break;
+			}
+		}
+		if (d == ndev - 1) {
+			z_next = znum;
+		}
+		if (z_next == z_lo) {
+			continue;
+		}
+		struct shard_job *j = &jobs[njobs++];
+		memset(j, 0, sizeof(*j));
+		j->plan = plan_for(dev[d], L, qnum, qvals, t);
+		j->coefA = coefA; j->coefB = coefB; j->a = params->a; j->bessel = bessel;
+		j->mult = params->mult; j->peak = params->peak;
+		j->znum = znum; j->z_lo = z_lo; j->z_hi = z_next;
+		j->idx32 = idx32; j->idx64 = idx64; j->nout = nout;
+		j->scores = scores; j->c1 = c1; j->c2 = c2;
+	}
+	if (njobs == 1) {
+		shard_main(&jobs[0]);
+	} else {
+		for (int k = 0; k < njobs; k++) {
+			if (pthread_create(&threads[k], NULL, shard_main, &jobs[k]) != 0) {
+				ERROR_MSG("pthread_create failed");
+			}
+		}
+		for (int k = 0; k < njobs; k++) {
+			pthread_join(threads[k], NULL);
+		}
+	}
+	for (int k = 0; k < njobs; k++) {
+		if (jobs[k].rc != 0) {
+			fprintf(stderr, "[Error] sxs_compute_saxs_scores: CUDA layer failed: %s\n", sxs_cuda_last_error());
+			exit(EXIT_FAILURE);
+		}
+	}
+	free(per_z);
+	free(bessel);
+	free(coefA);
+	free(coefB);
+}
+
+void sxs_compute_saxs_scores(double *scores_list, double *c1_list, double *c2_list, int *index_list, int nout,
+                             struct sxs_spf_full *A, struct sxs_spf_full *B, struct sxs_opt_params *params,
+                             double *qvals, int qnum, double *zvals, int znum, int L, int skip)
+{
+	(void)skip;
+	score_impl(scores_list, c1_list, c2_list, index_list, NULL, nout, A, B, params, qvals, qnum, zvals, znum, L);
+}
+
+void sxs_compute_saxs_scores64(double *scores_list, double *c1_list, double *c2_list, const long long *index_list,
+                               long long nout, struct sxs_spf_full *A, struct sxs_spf_full *B,
+                               struct sxs_opt_params *params, double *qvals, int qnum, double *zvals, int znum,
+                               int L, int skip)
+{
+	(void)skip;
+	score_impl(scores_list, c1_list, c2_list, NULL, index_list, nout, A, B, params, qvals, qnum, zvals, znum, L);
+}

@@ -1,0 +1,187 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfmftsaxs.so) against
+  (a) the committed golden fixtures — reference goldens and full-precision outputs of the compiled reference,
+  (b) the compiled reference itself (oracle/_ref/libsxsref.so) when it travelled to the box.
+Tolerances: north_star asks chi, c1, c2 within 1e-6 relative in FP64; coefficient stages are held to 1e-9
+of their scale.  All tests need a CUDA device (-m gpu).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from libfmftsaxs_b200 import capi
+import refso
+from golden import proto_cross_terms as proto
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+MAP = os.path.join(GOLD, "pdb_formfactor_mapping_clean.prm")
+PRM = os.path.join(GOLD, "atoms.prm")
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # north_star: relative, FP64
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+
+
+@pytest.fixture(scope="module")
+def FC():
+    return np.load(os.path.join(GOLD, "fit_cases.npz"))
+
+
+def names(a):
+    return [x.decode() for x in a]
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def test_device_present():
+    assert capi.device_count() >= 1
+
+
+@pytest.mark.parametrize("mol", ["rec", "lig", "dimer"])
+def test_expand_matches_reference(G, mol):
+    """K1 vs atom_grp2spf_inplace of the compiled reference (same SASA fractions fed to both)"""
+    q, L = G["qvals"], int(G["L"])
+    coef, rm, _ = capi.expand(MAP, G[mol + "_xyz"], names(G[mol + "_res"]), names(G[mol + "_atm"]), G[mol + "_radius"],
+                              q, L, sa=G[mol + "_sa"], water_mode=1)
+    ref = G[mol + "_coef"]
+    assert rm == pytest.approx(float(G[mol + "_rm"]), rel=1e-15)
+    for c in range(3):
+        scale = np.abs(ref[c]).max(axis=(1, 2), keepdims=True)  # per q
+        assert np.max(np.abs(coef[c] - ref[c]) / scale) < 1e-9
+
+
+def test_expand_ref_spf_golden(G):
+    """the reference's own test_pdb2spf (tests/saxs_test.c:59-127): rel 1e-3 against ref_spf on V and D;
+    W also depends on libmol2's SASA and is checked at 1e-3 of its scale (SASA)."""
+    q, L = G["qvals"], int(G["L"])
+    coef, rm, _ = capi.expand(MAP, G["rec_xyz"], names(G["rec_res"]), names(G["rec_atm"]), G["rec_radius"], q, L,
+                              water_mode=2)
+    assert abs(rm - G["ref_spf_header"][2]) < 5e-5
+    ref = G["ref_spf"]
+    for c in range(2):
+        mine = coef[c]
+        r = ref[:, :, 2 * c:2 * c + 2]
+        nz = (np.abs(mine) > 0) & (np.abs(r) > 0)
+        assert np.max(np.abs((r - mine)[nz] / r[nz])) < 1e-3
+    w = ref[:, :, 4:6]
+    assert np.max(np.abs(coef[2] - w)) / np.abs(w).max() < 1e-3
+
+
+def test_profile_from_spf(G):
+    """test_sxs_profile_from_spf (tests/saxs_test.c:129-175): rel 1e-6 vs ref_profile"""
+    q, L = G["qvals"], int(G["L"])
+    i, e = capi.profile_from_spf(G["rec_coef"], L, float(G["rec_rm"]), q, 1.0, 1.0)
+    assert relmax(i, G["profile_in"]) < 1e-12
+    assert relmax(i, G["ref_profile"][:, 1]) < 1e-6
+    assert relmax(e, G["ref_profile"][:, 2]) < 1e-6
+
+
+def test_fit_kernel_against_reference_lbfgsb(G, FC):
+    """K4 alone on 4052 cross-term profiles vs the vendored L-BFGS-B of the reference"""
+    q, a, scal = G["qvals"], G["a"], G["scal"]
+    X = np.concatenate([FC["X52"], proto.perturbed_family(FC["X52"], 4000, 1)])
+    want = np.concatenate([FC["fit52"], FC["fit_family"]])
+    got = capi.cuda_fit_profiles(X, a, q, scal[1], scal[2], rescale=True)
+    assert relmax(got[:, 0], want[:, 0]) < TOL
+    assert relmax(got[:, 1], want[:, 1]) < TOL
+    assert np.max(np.abs(got[:, 2] - want[:, 2])) < TOL * 4
+    # same trajectory: the number of objective evaluations agrees for nearly every fit (device exp() and
+    # glibc exp() differ in the last ulp now and then, which can move a line search by one evaluation)
+    assert np.mean(got[:, 3] == want[:, 3]) > 0.99
+
+
+def test_cross_terms_z40(G, FC):
+    """K2+K3 stage output vs the numpy restatement driven by reference tables"""
+    q, L = G["qvals"], int(G["L"])
+    plan = capi.Plan(L, q)
+    plan.set_molecules(G["rec_coef"], G["lig_coef"])
+    plan.set_experiment(G["a"], G["scal"][1], G["scal"][2])
+    plan.set_translations([40.0])
+    X = plan.cross_terms(G["z40_index"])
+    scale = np.abs(FC["X52"]).max(axis=2, keepdims=True)
+    assert np.max(np.abs(X - FC["X52"]) / scale) < 1e-10
+    plan.close()
+
+
+def test_scores_z40_ref_chi(G):
+    """score_conformations (tests/saxs_test.c:177-363) through sxs_compute_saxs_scores"""
+    q, L = G["qvals"], int(G["L"])
+    s, c1, c2 = capi.scores(G["z40_index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, [40.0], L)
+    assert relmax(s, G["z40_scores"]) < TOL
+    assert relmax(c1, G["z40_c1"]) < TOL
+    assert np.max(np.abs(c2 - G["z40_c2"])) < TOL * 4
+    rc = G["ref_chi"]
+    assert np.array_equal(rc[:, 0].astype(int), G["z40_ft"])
+    assert np.max(np.abs(s - rc[:, 1])) < 1e-3
+    assert np.max(np.abs(c1 - rc[:, 2])) < 1e-3
+    assert np.max(np.abs(c2 - rc[:, 3])) < 1e-3
+
+
+def test_scores_six_z_with_fft_branch_cells(G):
+    """1131 real rows over 6 z steps; some cells hold >= 30 rows (the reference's FFTW branch)"""
+    q, L = G["qvals"], int(G["L"])
+    s, c1, c2 = capi.scores(G["z6_index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, G["z6_zvals"], L)
+    assert relmax(s, G["z6_scores"]) < TOL
+    assert relmax(c1, G["z6_c1"]) < TOL
+    assert np.max(np.abs(c2 - G["z6_c2"])) < TOL * 4
+
+
+def test_scores_edge_cases(G):
+    """empty list, rows outside the z table keep incoming values, duplicates, shuffled order"""
+    q, L = G["qvals"], int(G["L"])
+    nb, N = L + 1, 2 * L + 1
+    args = (G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, [40.0], L)
+    s, c1, c2 = capi.scores(np.zeros(0, dtype=np.int32), *args)
+    assert len(s) == 0
+    idx = G["z40_index"].copy()
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(idx))
+    big = np.concatenate([idx[perm], idx[:7], [nb * nb * N ** 3 * 3 + 11, -5]]).astype(np.int32)
+    init = (np.full(len(big), 7.0), np.full(len(big), 8.0), np.full(len(big), 9.0))
+    s, c1, c2 = capi.scores(big, *args, init=init)
+    n = len(idx)
+    assert relmax(s[:n], G["z40_scores"][perm]) < TOL
+    assert np.array_equal(s[n:n + 7], s[:n][np.argsort(perm)][:7])
+    assert s[-1] == 7.0 and c1[-1] == 8.0 and c2[-1] == 9.0
+    assert s[-2] == 7.0 and c1[-2] == 8.0 and c2[-2] == 9.0
+    # 64-bit entry point gives the same numbers
+    s64, c164, c264 = capi.scores(idx.astype(np.int64), *args)
+    assert np.array_equal(s64, capi.scores(idx, *args)[0])
+
+
+def test_minimize_score(G):
+    """minimize_score (tests/saxs_test.c:365-407): fitted profile of the native dimer"""
+    q, L = G["qvals"], int(G["L"])
+    i, e, o = capi.fitted_profile(G["dimer_coef"], L, G["a_dimer"], G["scal_dimer"], q)
+    assert relmax(i, G["fitted_in"]) < TOL
+    assert relmax(o, G["fitted_out3"]) < TOL
+    # the reference's golden file (4 decimals); the compiled reference itself sits 1.03e-6 from it
+    assert relmax(i, G["ref_fitted_profile"][:, 1]) < 3e-6
+
+
+@pytest.mark.skipif(not refso.available(), reason="compiled reference (oracle/_ref) not present")
+def test_live_reference_random_rows(G):
+    """fresh random grid points, scored by the compiled reference on this box's CPU and by the GPU"""
+    q, L = G["qvals"], int(G["L"])
+    nb, N = L + 1, 2 * L + 1
+    rng = np.random.default_rng(11)
+    zv = [17.0, 33.5, 80.0]
+    n = 60
+    dig = np.stack([rng.integers(0, 3, n), rng.integers(1, nb - 1, n), rng.integers(1, nb - 1, n), rng.integers(0, N, n),
+                    rng.integers(0, N, n), rng.integers(0, N, n)], 1)
+    dig[: n // 2, 1:3] = dig[0, 1:3]  # crowd one (b1, b2) pair so that a cell exceeds 30 rows
+    dig[: n // 2, 0] = 1
+    idx = (((((dig[:, 0] * nb + dig[:, 1]) * nb + dig[:, 2]) * N + dig[:, 3]) * N + dig[:, 4]) * N + dig[:, 5]).astype(np.int32)
+    want = refso.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
+    got = capi.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
+    assert relmax(got[0], want[0]) < TOL
+    assert relmax(got[1], want[1]) < TOL
+    assert np.max(np.abs(got[2] - want[2])) < TOL * 4
