@@ -241,6 +241,8 @@ def run_product(args):
     ktimes = plan.kernel_times()
     plan.set_profiling(False)
     stats = plan.stats()
+    hist = plan.fit_evaluations()
+    nfg_mean = float((hist * np.arange(64)).sum() / max(1, hist.sum()))
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -314,6 +316,9 @@ def run_product(args):
                         "steps": e2e_steps, "api": "sxs_compute_saxs_scores (flat adapter), pinned host buffers"},
                 "gpu_launches": int(stats["launches"] * args.steps),
                 "kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
+                "fit_evaluations": {"mean": nfg_mean, "p50": int(np.searchsorted(np.cumsum(hist), 0.5 * hist.sum())),
+                                    "p99": int(np.searchsorted(np.cumsum(hist), 0.99 * hist.sum())),
+                                    "max_bin": int(np.flatnonzero(hist).max()) if hist.sum() else 0},
                 "roofline": roofline, "cpu_baseline": cpu, "resident_equals_host_path": same}
         print(json.dumps(line))
     if world > 1:

@@ -82,6 +82,10 @@ int sxs_cuda_plan_score_dev_i64(sxs_cuda_plan *plan, const long long *d_index, l
  * [2] kernel launches, [3] objective evaluations summed over fits, [4] z groups. */
 int sxs_cuda_plan_stats(const sxs_cuda_plan *plan, long long *stats5);
 
+/* Histogram of objective evaluations per fit over the distinct points of the last score call
+ * (hist64[n] = fits that took n evaluations, bin 63 = 63 or more; the reference's isave[33]). */
+int sxs_cuda_plan_fit_evaluations(sxs_cuda_plan *plan, long long *hist64);
+
 /* Device-side timing of the kernel classes of subsequent score calls, with CUDA events recorded on the
  * launching stream: ms5/launches5 = {0 key sort + distinct points, 1 T-matrix + translation, 2 cross terms
  * (K3), 3 fit (K4), 4 scatter}.  kernel_times() waits for the recorded events and resets the counters. */

@@ -48,6 +48,7 @@ def lib():
         _lib.sxs_cuda_plan_score_dev_i64.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.sxs_cuda_plan_stats.argtypes = [C.c_void_p, _llp]
+        _lib.sxs_cuda_plan_fit_evaluations.argtypes = [C.c_void_p, _llp]
         _lib.sxs_cuda_plan_set_profiling.argtypes = [C.c_void_p, C.c_int]
         _lib.sxs_cuda_plan_kernel_times.argtypes = [C.c_void_p, _dp, _llp]
         _lib.sxs_cuda_plan_cross_terms_i32.argtypes = [C.c_void_p, _ip, C.c_longlong, _dp]
@@ -318,6 +319,12 @@ class Plan:
         _check(lib().sxs_cuda_plan_kernel_times(self._h, ms, n), "kernel_times")
         names = ["sort", "translate", "cross", "fit", "scatter"]
         return {k: (ms[i], n[i]) for i, k in enumerate(names)}
+
+    def fit_evaluations(self):
+        """histogram of objective evaluations per fit of the last score call"""
+        h = (C.c_longlong * 64)()
+        _check(lib().sxs_cuda_plan_fit_evaluations(self._h, h), "fit_evaluations")
+        return np.array(list(h))
 
     def stats(self):
         st = (C.c_longlong * 5)()

@@ -3,8 +3,8 @@
  * Follows src/min_saxs.c operation for operation: sxs_best_scale (:261-319) gives the optimal linear
  * scale k for the trial (c1, c2), gradient() (:3-105) then accumulates f and df/dc with k frozen.
  * Both walk the q nodes once with a piecewise-linear model between nodes (q_{-1} = -1).
- * The six cross terms are read through a stride so that a warp's loads are coalesced
- * (layout X[(q*6 + c) * stride + point]); the peak rescale of sxs_fit_params (:170-188) is applied
+ * The six cross terms are read through two strides (between terms, between q nodes) so that the same
+ * code serves a point-major row (stride 1, qstride 6) and a point-minor column; the peak rescale of sxs_fit_params (:170-188) is applied
  * on the fly as x*scale, which rounds exactly like the reference's in-place `*= scale`.
  *
  * Compiled with -fmad=false (see lbfgsb_n2m3.h); plain C so the CPU tests can include it.
@@ -23,8 +23,9 @@
 #endif
 
 struct sxs_fit_ctx {
-	const double *x;      /* cross terms of this point: x[(q*6 + c) * stride] */
-	long stride;
+	const double *x;      /* cross terms of this point: x[q*qstride + c*stride] */
+	long stride;          /* between the six terms of one q */
+	long qstride;         /* between q nodes */
 	const double *a;      /* compressed experiment, a[q*6 + 0..5] (src/min_saxs.c:353-389) */
 	const double *qvals;
 	int qnum;
@@ -34,7 +35,26 @@ struct sxs_fit_ctx {
 
 enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 
-#define SXS_X(ctx, q, c) ((ctx)->x[((long)(q) * 6 + (c)) * (ctx)->stride] * (ctx)->scale)
+#define SXS_X(ctx, q, c) ((ctx)->x[(long)(q) * (ctx)->qstride + (long)(c) * (ctx)->stride] * (ctx)->scale)
+
+/* The six scaled terms of node q.  With SXS_ROWMAJOR_VEC (CUDA build, point-major rows x[q*6 + c],
+ * 16-byte aligned) they come in as three 16-byte loads; the values and their use are identical. */
+#if defined(SXS_ROWMAJOR_VEC) && defined(__CUDA_ARCH__)
+#define SXS_LOAD6(ctx, q, vv, vd, vw, dd, dw, ww)                                       \
+	do {                                                                               \
+		const double2 *r_ = reinterpret_cast<const double2 *>((ctx)->x + (long)(q) * 6); \
+		const double2 p0_ = r_[0], p1_ = r_[1], p2_ = r_[2];                             \
+		vv = p0_.x * (ctx)->scale; vd = p0_.y * (ctx)->scale;                            \
+		vw = p1_.x * (ctx)->scale; dd = p1_.y * (ctx)->scale;                            \
+		dw = p2_.x * (ctx)->scale; ww = p2_.y * (ctx)->scale;                            \
+	} while (0)
+#else
+#define SXS_LOAD6(ctx, q, vv, vd, vw, dd, dw, ww)                                       \
+	do {                                                                               \
+		vv = SXS_X(ctx, q, SXS_VV); vd = SXS_X(ctx, q, SXS_VD); vw = SXS_X(ctx, q, SXS_VW); \
+		dd = SXS_X(ctx, q, SXS_DD); dw = SXS_X(ctx, q, SXS_DW); ww = SXS_X(ctx, q, SXS_WW); \
+	} while (0)
+#endif
 
 /* src/min_saxs.c:261-319 */
 SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, double c2)
@@ -45,8 +65,9 @@ SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, doubl
 	const double corr = -mult * (c1 * c1 - 1.0);
 	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
 
-	double in_prev = SXS_X(ctx, 0, SXS_VV) - G * SXS_X(ctx, 0, SXS_VD) + c2 * SXS_X(ctx, 0, SXS_VW) +
-	                 G * G * SXS_X(ctx, 0, SXS_DD) - G * c2 * SXS_X(ctx, 0, SXS_DW) + c2 * c2 * SXS_X(ctx, 0, SXS_WW);
+	double xvv, xvd, xvw, xdd, xdw, xww;
+	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
+	double in_prev = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 	const double c1_cube = c1 * c1 * c1;
 	double q_prev = -1.0;
 	double up = 0.0, down = 0.0;
@@ -54,9 +75,8 @@ SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, doubl
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
 		G = c1_cube * exp(corr * q_cur * q_cur);
-		const double in = SXS_X(ctx, i, SXS_VV) - G * SXS_X(ctx, i, SXS_VD) + c2 * SXS_X(ctx, i, SXS_VW) +
-		                  G * G * SXS_X(ctx, i, SXS_DD) - G * c2 * SXS_X(ctx, i, SXS_DW) +
-		                  c2 * c2 * SXS_X(ctx, i, SXS_WW);
+		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
+		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 		const double tan = (in - in_prev) / (q_cur - q_prev);
 		const double buf = in - tan * q_cur;
 
@@ -82,11 +102,11 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
 	double G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q[0] * q[0]);
 
-	double in_prev = SXS_X(ctx, 0, SXS_VV) - G * SXS_X(ctx, 0, SXS_VD) + c2 * SXS_X(ctx, 0, SXS_VW) +
-	                 G * G * SXS_X(ctx, 0, SXS_DD) - G * c2 * SXS_X(ctx, 0, SXS_DW) + c2 * c2 * SXS_X(ctx, 0, SXS_WW);
-	double in_der_c1_prev = -G_der * SXS_X(ctx, 0, SXS_VD) + 2.0 * G * G_der * SXS_X(ctx, 0, SXS_DD) -
-	                        G_der * c2 * SXS_X(ctx, 0, SXS_DW);
-	double in_der_c2_prev = SXS_X(ctx, 0, SXS_VW) - G * SXS_X(ctx, 0, SXS_DW) + 2.0 * c2 * SXS_X(ctx, 0, SXS_WW);
+	double xvv, xvd, xvw, xdd, xdw, xww;
+	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
+	double in_prev = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
+	double in_der_c1_prev = -G_der * xvd + 2.0 * G * G_der * xdd - G_der * c2 * xdw;
+	double in_der_c2_prev = xvw - G * xdw + 2.0 * c2 * xww;
 
 	double q_prev = -1.0;
 	double score = 0.0;
@@ -97,8 +117,7 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 		G = c1_cube * exp(corr * q_cur * q_cur);
 		G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q_cur * q_cur);
 
-		const double xvv = SXS_X(ctx, i, SXS_VV), xvd = SXS_X(ctx, i, SXS_VD), xvw = SXS_X(ctx, i, SXS_VW);
-		const double xdd = SXS_X(ctx, i, SXS_DD), xdw = SXS_X(ctx, i, SXS_DW), xww = SXS_X(ctx, i, SXS_WW);
+		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
 
 		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 		const double in_der_c1 = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);

@@ -14,46 +14,35 @@
 #define SXS_C1_DEFAULT 1.0
 #define SXS_C2_DEFAULT 0.0
 
-SXS_HD void sxs_fit_point(const double *x, long stride, const double *a, const double *qvals, int qnum,
+/* peak / I(0) of sxs_fit_params, in the reference's summation order (src/min_saxs.c:170-179) */
+SXS_HD double sxs_fit_rescale(const struct sxs_fit_ctx *ctx_unit, double peak)
+{
+	const double i0 = SXS_X(ctx_unit, 0, SXS_VV) + SXS_X(ctx_unit, 0, SXS_DD) + SXS_X(ctx_unit, 0, SXS_WW) +
+	                  SXS_X(ctx_unit, 0, SXS_VW) - SXS_X(ctx_unit, 0, SXS_VD) - SXS_X(ctx_unit, 0, SXS_DW);
+	return peak / i0;
+}
+
+/* Serial form (one fit start to finish); the CUDA kernel interleaves lb_step() and the evaluation
+ * across the lanes of a warp instead, see k_fit in sxs_exact.cu. */
+SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const double *a, const double *qvals, int qnum,
                           double mult, double peak, double *score, double *c1, double *c2, int *nfg)
 {
 	struct sxs_fit_ctx ctx;
 	ctx.x = x;
 	ctx.stride = stride;
+	ctx.qstride = qstride;
 	ctx.a = a;
 	ctx.qvals = qvals;
 	ctx.qnum = qnum;
 	ctx.mult = mult;
 	ctx.scale = 1.0;
-	double i0 = SXS_X(&ctx, 0, SXS_VV) + SXS_X(&ctx, 0, SXS_DD) + SXS_X(&ctx, 0, SXS_WW) + SXS_X(&ctx, 0, SXS_VW) -
-	            SXS_X(&ctx, 0, SXS_VD) - SXS_X(&ctx, 0, SXS_DW);
-	ctx.scale = peak / i0;
+	ctx.scale = sxs_fit_rescale(&ctx, peak);
 
 	struct lb_state st;
-	st.x[1] = SXS_C1_DEFAULT; st.x[2] = SXS_C2_DEFAULT;
-	st.l[1] = SXS_C1_LOWER;   st.l[2] = SXS_C2_LOWER;
-	st.u[1] = SXS_C1_UPPER;   st.u[2] = SXS_C2_UPPER;
-	st.g[1] = 0.0; st.g[2] = 0.0;
-	st.f = 0.0;
-	/* the reference zeroes its whole workspace before every fit (src/min_saxs.c:217-221) */
-	for (int i = 0; i <= LB_N; i++) {
-		for (int j = 0; j <= LB_M; j++) { st.ws[i][j] = 0.0; st.wy[i][j] = 0.0; }
-		st.z[i] = st.r[i] = st.d[i] = st.t[i] = st.xp[i] = 0.0;
-		st.index[i] = st.iwhere[i] = st.indx2[i] = 0;
+	lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
+	while (lb_step(&st, 1e-5) == LB_NEED_EVAL) {
+		sxs_fit_eval(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 	}
-	for (int i = 0; i <= LB_M; i++) {
-		for (int j = 0; j <= LB_M; j++) { st.sy[i][j] = 0.0; st.ss[i][j] = 0.0; st.wt[i][j] = 0.0; }
-	}
-	for (int i = 0; i <= LB_M2; i++) {
-		for (int j = 0; j <= LB_M2; j++) { st.wn[i][j] = 0.0; st.wn1[i][j] = 0.0; }
-	}
-	for (int i = 0; i <= 8 * LB_M; i++) { st.wa[i] = 0.0; }
-	st.brackt = 0; st.stage = 0; st.ls_task = LS_START;
-	st.ginit = st.gtest = st.gx = st.gy = st.finit = st.fx = st.fy = 0.0;
-	st.stx = st.sty = st.stmin = st.stmax = st.width = st.width1 = 0.0;
-
-	LB_MINIMIZE(&st, LB_EVAL(&ctx, &st), 1e+7, 1e-5);
-
 	*score = sqrt(st.f);
 	*c1 = st.x[1];
 	*c2 = st.x[2];

@@ -28,6 +28,18 @@
 #endif
 #endif
 
+/* The optimiser is control-flow heavy and tiny in arithmetic.  On the GPU it is kept as real
+ * (non-inlined) functions with rolled loops: fully inlined and unrolled it compiles to ~20 000 SASS
+ * instructions (330 KB), and the divergent lanes of a warp then stall on instruction-cache misses
+ * (ncu: 63 % of warp cycles in "no instruction"); the objective evaluation stays inlined. */
+#ifdef __CUDACC__
+#define LB_FN __host__ __device__ __noinline__
+#define LB_NOUNROLL _Pragma("unroll 1")
+#else
+#define LB_FN static
+#define LB_NOUNROLL
+#endif
+
 #define LB_N 2
 #define LB_M 3
 #define LB_M2 (2 * LB_M)
@@ -58,6 +70,7 @@ struct lb_state {
 	int index[LB_N + 1], iwhere[LB_N + 1], indx2[LB_N + 1];
 	double theta, fold, dnorm, gd, gdold, stp, stpmx, sbgnrm, dtd, tol;
 	int col, head, itail, iupdat, updatd, iback, ifun, iter, nfgv, nfree, nact, ileave, nenter, nseg, wrk;
+	int phase; /* enum lb_phase: where lb_step() resumes */
 	/* Moré–Thuente search state */
 	int brackt, stage, ls_task;
 	double ginit, gtest, gx, gy, finit, fx, fy, stx, sty, stmin, stmax, width, width1;
@@ -79,13 +92,13 @@ SXS_HD void lb_reset_memory(struct lb_state *s)
 /* Cholesky factor (upper) of the n x n block of `a` whose (1,1) sits at a[r0+1][c0+1];
  * LINPACK dpofa, lbfgsb/src/linpack.c:11-109.  a is addressed a[row][col]. */
 #define LB_DPOFA(NAME, DIM)                                                                           \
-	SXS_HD int NAME(double (*a)[DIM + 1], int off, int n)                                              \
+	LB_FN int NAME(double (*a)[DIM + 1], int off, int n)                                              \
 	{                                                                                                 \
-		for (int j = 1; j <= n; j++) {                                                                \
+		LB_NOUNROLL for (int j = 1; j <= n; j++) {                                                                \
 			double sacc = 0.0;                                                                        \
-			for (int k = 1; k <= j - 1; k++) {                                                        \
+			LB_NOUNROLL for (int k = 1; k <= j - 1; k++) {                                                        \
 				double dot = 0.0;                                                                     \
-				for (int i = 1; i <= k - 1; i++) {                                                    \
+				LB_NOUNROLL for (int i = 1; i <= k - 1; i++) {                                                    \
 					dot += a[off + i][off + k] * a[off + i][off + j];                                 \
 				}                                                                                     \
 				double tt = a[off + k][off + j] - dot;                                                \
@@ -107,18 +120,18 @@ LB_DPOFA(lb_dpofa_2m, LB_M2)
 /* Triangular solves with an upper-triangular factor stored in t[row][col] (LINPACK dtrsl,
  * lbfgsb/src/linpack.c:111-297): job 11 solves trans(T) x = b, job 01 solves T x = b. */
 #define LB_DTRSL(NAME, DIM)                                                                           \
-	SXS_HD int NAME(double (*t)[DIM + 1], int n, double *b, int job)                                   \
+	LB_FN int NAME(double (*t)[DIM + 1], int n, double *b, int job)                                   \
 	{                                                                                                 \
-		for (int i = 1; i <= n; i++) {                                                                \
+		LB_NOUNROLL for (int i = 1; i <= n; i++) {                                                                \
 			if (t[i][i] == 0.0) {                                                                     \
 				return i;                                                                             \
 			}                                                                                         \
 		}                                                                                             \
 		if (job == 11) {                                                                              \
 			b[1] /= t[1][1];                                                                          \
-			for (int j = 2; j <= n; j++) {                                                            \
+			LB_NOUNROLL for (int j = 2; j <= n; j++) {                                                            \
 				double dot = 0.0;                                                                     \
-				for (int i = 1; i <= j - 1; i++) {                                                    \
+				LB_NOUNROLL for (int i = 1; i <= j - 1; i++) {                                                    \
 					dot += t[i][j] * b[i];                                                            \
 				}                                                                                     \
 				b[j] -= dot;                                                                          \
@@ -126,11 +139,11 @@ LB_DPOFA(lb_dpofa_2m, LB_M2)
 			}                                                                                         \
 		} else { /* job == 01 */                                                                      \
 			b[n] /= t[n][n];                                                                          \
-			for (int jj = 2; jj <= n; jj++) {                                                         \
+			LB_NOUNROLL for (int jj = 2; jj <= n; jj++) {                                                         \
 				int j = n - jj + 1;                                                                   \
 				double temp = -b[j + 1];                                                              \
 				if (temp != 0.0) {                                                                    \
-					for (int i = 1; i <= j; i++) {                                                    \
+					LB_NOUNROLL for (int i = 1; i <= j; i++) {                                                    \
 						b[i] += temp * t[i][j + 1];                                                   \
 					}                                                                                 \
 				}                                                                                     \
@@ -144,7 +157,7 @@ LB_DTRSL(lb_dtrsl_2m, LB_M2)
 
 /* Product of the 2m x 2m middle matrix of the compact L-BFGS formula with a 2*col vector
  * (subalgorithms.c bmv, :120-259). */
-SXS_HD int lb_bmv(const struct lb_state *s, const double *v, double *p)
+LB_FN int lb_bmv(const struct lb_state *s, const double *v, double *p)
 {
 	const int col = s->col;
 	if (col == 0) {
@@ -153,9 +166,11 @@ SXS_HD int lb_bmv(const struct lb_state *s, const double *v, double *p)
 	/* solve [ D^(1/2)  O ] [ p1 ] = [ v1 ]
 	 *       [ -L*D^(-1/2) J ] [ p2 ]   [ v2 ]  */
 	p[col + 1] = v[col + 1];
+	LB_NOUNROLL
 	for (int i = 2; i <= col; i++) {
 		int i2 = col + i;
 		double sum = 0.0;
+		LB_NOUNROLL
 		for (int k = 1; k <= i - 1; k++) {
 			sum += s->sy[i][k] * v[k] / s->sy[k][k];
 		}
@@ -165,6 +180,7 @@ SXS_HD int lb_bmv(const struct lb_state *s, const double *v, double *p)
 	if (info != 0) {
 		return info;
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= col; i++) {
 		p[i] = v[i] / sqrt(s->sy[i][i]);
 	}
@@ -174,11 +190,14 @@ SXS_HD int lb_bmv(const struct lb_state *s, const double *v, double *p)
 	if (info != 0) {
 		return info;
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= col; i++) {
 		p[i] = -p[i] / sqrt(s->sy[i][i]);
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= col; i++) {
 		double sum = 0.0;
+		LB_NOUNROLL
 		for (int k = i + 1; k <= col; k++) {
 			sum += s->sy[k][i] * p[col + k] / s->sy[i][i];
 		}
@@ -188,9 +207,10 @@ SXS_HD int lb_bmv(const struct lb_state *s, const double *v, double *p)
 }
 
 /* Heap extraction of the next breakpoint (subalgorithms.c hpsolb, :1816-1901). */
-SXS_HD void lb_hpsolb(int n, double *t, int *iorder, int iheap)
+LB_FN void lb_hpsolb(int n, double *t, int *iorder, int iheap)
 {
 	if (iheap == 0) {
+		LB_NOUNROLL
 		for (int k = 2; k <= n; k++) {
 			double ddum = t[k];
 			int indxin = iorder[k];
@@ -215,6 +235,7 @@ SXS_HD void lb_hpsolb(int n, double *t, int *iorder, int iheap)
 		int indxou = iorder[1];
 		double ddum = t[n];
 		int indxin = iorder[n];
+		LB_NOUNROLL
 		for (;;) {
 			int j = i + i;
 			if (j <= n - 1) {
@@ -238,9 +259,10 @@ SXS_HD void lb_hpsolb(int n, double *t, int *iorder, int iheap)
 }
 
 /* Projected-gradient sup-norm (subalgorithms.c projgr, :1513-1560); both variables are boxed. */
-SXS_HD double lb_projgr(const struct lb_state *s)
+LB_FN double lb_projgr(const struct lb_state *s)
 {
 	double sbgnrm = 0.0;
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		double gi = s->g[i];
 		if (gi < 0.0) {
@@ -256,7 +278,7 @@ SXS_HD double lb_projgr(const struct lb_state *s)
 /* Generalised Cauchy point (subalgorithms.c cauchy, :261-818).  Workspace split of wa as in
  * mainlb: p = wa[1..2m], c = wa[2m+1..4m], wbp = wa[4m+1..6m], v = wa[6m+1..8m].
  * Breakpoint times share storage with s->t, the order array with s->indx2 (as mainlb passes them). */
-SXS_HD int lb_cauchy(struct lb_state *s)
+LB_FN int lb_cauchy(struct lb_state *s)
 {
 	double *p = &s->wa[0], *c = &s->wa[2 * LB_M], *wbp = &s->wa[4 * LB_M], *v = &s->wa[6 * LB_M];
 	double *t = s->t, *d = s->d, *xcp = s->z;
@@ -265,6 +287,7 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 	const double theta = s->theta;
 
 	if (s->sbgnrm <= 0.0) {
+		LB_NOUNROLL
 		for (int i = 1; i <= LB_N; i++) {
 			xcp[i] = s->x[i];
 		}
@@ -279,9 +302,11 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 	double f1 = 0.0;
 	double tl = 0.0, tu = 0.0;
 
+	LB_NOUNROLL
 	for (int i = 1; i <= col2; i++) {
 		p[i] = 0.0;
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		double neggi = -s->g[i];
 		if (iwhere[i] != 3 && iwhere[i] != -1) {
@@ -310,6 +335,7 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 		} else {
 			d[i] = neggi;
 			f1 -= neggi * neggi;
+			LB_NOUNROLL
 			for (int j = 1; j <= col; j++) {
 				p[j] += s->wy[i][pointr] * neggi;
 				p[col + j] += s->ws[i][pointr] * neggi;
@@ -341,16 +367,19 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 		}
 	}
 	if (theta != 1.0) {
+		LB_NOUNROLL
 		for (int j = 1; j <= col; j++) {
 			p[col + j] = theta * p[col + j];
 		}
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		xcp[i] = s->x[i];
 	}
 	if (nbreak == 0 && nfree == LB_N + 1) {
 		return 0;
 	}
+	LB_NOUNROLL
 	for (int j = 1; j <= col2; j++) {
 		c[j] = 0.0;
 	}
@@ -362,6 +391,7 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 			return info;
 		}
 		double dot = 0.0;
+		LB_NOUNROLL
 		for (int j = 1; j <= col2; j++) {
 			dot += v[j] * p[j];
 		}
@@ -376,6 +406,7 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 		int nleft = nbreak;
 		int iter = 1;
 		double tj = 0.0;
+		LB_NOUNROLL
 		for (;;) {
 			double tj0 = tj;
 			int ibp;
@@ -423,11 +454,13 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 			f2 -= theta * dibp2;
 			if (col > 0) {
 				if (dt != 0.0) {
+					LB_NOUNROLL
 					for (int j = 1; j <= col2; j++) {
 						c[j] += dt * p[j];
 					}
 				}
 				int pointr = s->head;
+				LB_NOUNROLL
 				for (int j = 1; j <= col; j++) {
 					wbp[j] = s->wy[ibp][pointr];
 					wbp[col + j] = theta * s->ws[ibp][pointr];
@@ -438,17 +471,21 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 					return info;
 				}
 				double wmc = 0.0, wmp = 0.0, wmw = 0.0;
+				LB_NOUNROLL
 				for (int j = 1; j <= col2; j++) {
 					wmc += c[j] * v[j];
 				}
+				LB_NOUNROLL
 				for (int j = 1; j <= col2; j++) {
 					wmp += p[j] * v[j];
 				}
+				LB_NOUNROLL
 				for (int j = 1; j <= col2; j++) {
 					wmw += wbp[j] * v[j];
 				}
 				double mdibp = -dibp;
 				if (mdibp != 0.0) {
+					LB_NOUNROLL
 					for (int j = 1; j <= col2; j++) {
 						p[j] += mdibp * wbp[j];
 					}
@@ -476,12 +513,14 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 		}
 		tsum += dtm;
 		if (tsum != 0.0) {
+			LB_NOUNROLL
 			for (int i = 1; i <= LB_N; i++) {
 				xcp[i] += tsum * d[i];
 			}
 		}
 	}
 	if (col > 0 && dtm != 0.0) {
+		LB_NOUNROLL
 		for (int j = 1; j <= col2; j++) {
 			c[j] += dtm * p[j];
 		}
@@ -490,12 +529,13 @@ SXS_HD int lb_cauchy(struct lb_state *s)
 }
 
 /* Free/active bookkeeping at the Cauchy point (subalgorithms.c freev, :1741-1814). */
-SXS_HD void lb_freev(struct lb_state *s)
+LB_FN void lb_freev(struct lb_state *s)
 {
 	int *index = s->index, *indx2 = s->indx2, *iwhere = s->iwhere;
 	s->nenter = 0;
 	s->ileave = LB_N + 1;
 	if (s->iter > 0) {
+		LB_NOUNROLL
 		for (int i = 1; i <= s->nfree; i++) {
 			int k = index[i];
 			if (iwhere[k] > 0) {
@@ -503,6 +543,7 @@ SXS_HD void lb_freev(struct lb_state *s)
 				indx2[s->ileave] = k;
 			}
 		}
+		LB_NOUNROLL
 		for (int i = s->nfree + 1; i <= LB_N; i++) {
 			int k = index[i];
 			if (iwhere[k] <= 0) {
@@ -514,6 +555,7 @@ SXS_HD void lb_freev(struct lb_state *s)
 	s->wrk = (s->ileave < LB_N + 1) || (s->nenter > 0) || s->updatd;
 	s->nfree = 0;
 	int iact = LB_N + 1;
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		if (iwhere[i] <= 0) {
 			++s->nfree;
@@ -527,7 +569,7 @@ SXS_HD void lb_freev(struct lb_state *s)
 
 /* LEL^T factorisation of the indefinite subspace matrix (subalgorithms.c formk, :820-1303),
  * including its incremental update of the lower triangle of N kept in wn1. */
-SXS_HD int lb_formk(struct lb_state *s)
+LB_FN int lb_formk(struct lb_state *s)
 {
 	const int col = s->col, head = s->head, nsub = s->nfree;
 	const int *ind = s->index, *indx2 = s->indx2;
@@ -538,14 +580,18 @@ SXS_HD int lb_formk(struct lb_state *s)
 	if (s->updatd) {
 		if (s->iupdat > LB_M) {
 			/* shift old part of WN1 */
+			LB_NOUNROLL
 			for (int jy = 1; jy <= LB_M - 1; jy++) {
 				int js = LB_M + jy;
+				LB_NOUNROLL
 				for (int i = 0; i < LB_M - jy; i++) {
 					wn1[jy + i][jy] = wn1[jy + 1 + i][jy + 1];
 				}
+				LB_NOUNROLL
 				for (int i = 0; i < LB_M - jy; i++) {
 					wn1[js + i][js] = wn1[js + 1 + i][js + 1];
 				}
+				LB_NOUNROLL
 				for (int i = 0; i < LB_M - 1; i++) {
 					wn1[LB_M + 1 + i][jy] = wn1[LB_M + 2 + i][jy + 1];
 				}
@@ -560,13 +606,16 @@ SXS_HD int lb_formk(struct lb_state *s)
 			ipntr -= LB_M;
 		}
 		int jpntr = head;
+		LB_NOUNROLL
 		for (int jy = 1; jy <= col; jy++) {
 			int js = LB_M + jy;
 			double temp1 = 0.0, temp2 = 0.0, temp3 = 0.0;
+			LB_NOUNROLL
 			for (int k = pbegin; k <= pend; k++) {
 				int k1 = ind[k];
 				temp1 += s->wy[k1][ipntr] * s->wy[k1][jpntr];
 			}
+			LB_NOUNROLL
 			for (int k = dbegin; k <= dend; k++) {
 				int k1 = ind[k];
 				temp2 += s->ws[k1][ipntr] * s->ws[k1][jpntr];
@@ -584,9 +633,11 @@ SXS_HD int lb_formk(struct lb_state *s)
 			jpntr -= LB_M;
 		}
 		ipntr = head;
+		LB_NOUNROLL
 		for (int i = 1; i <= col; i++) {
 			int is2 = LB_M + i;
 			double temp3 = 0.0;
+			LB_NOUNROLL
 			for (int k = pbegin; k <= pend; k++) {
 				int k1 = ind[k];
 				temp3 += s->ws[k1][ipntr] * s->wy[k1][jpntr];
@@ -600,17 +651,21 @@ SXS_HD int lb_formk(struct lb_state *s)
 	}
 	/* modify the old parts in blocks (1,1) and (2,2) due to changes in the set of free variables */
 	int ipntr = head;
+	LB_NOUNROLL
 	for (int iy = 1; iy <= upcl; iy++) {
 		int is = LB_M + iy;
 		int jpntr = head;
+		LB_NOUNROLL
 		for (int jy = 1; jy <= iy; jy++) {
 			int js = LB_M + jy;
 			double temp1 = 0.0, temp2 = 0.0, temp3 = 0.0, temp4 = 0.0;
+			LB_NOUNROLL
 			for (int k = 1; k <= s->nenter; k++) {
 				int k1 = indx2[k];
 				temp1 += s->wy[k1][ipntr] * s->wy[k1][jpntr];
 				temp2 += s->ws[k1][ipntr] * s->ws[k1][jpntr];
 			}
+			LB_NOUNROLL
 			for (int k = s->ileave; k <= LB_N; k++) {
 				int k1 = indx2[k];
 				temp3 += s->wy[k1][ipntr] * s->wy[k1][jpntr];
@@ -624,14 +679,18 @@ SXS_HD int lb_formk(struct lb_state *s)
 	}
 	/* modify the old parts in block (2,1) */
 	ipntr = head;
+	LB_NOUNROLL
 	for (int is = LB_M + 1; is <= LB_M + upcl; is++) {
 		int jpntr = head;
+		LB_NOUNROLL
 		for (int jy = 1; jy <= upcl; jy++) {
 			double temp1 = 0.0, temp3 = 0.0;
+			LB_NOUNROLL
 			for (int k = 1; k <= s->nenter; k++) {
 				int k1 = indx2[k];
 				temp1 += s->ws[k1][ipntr] * s->wy[k1][jpntr];
 			}
+			LB_NOUNROLL
 			for (int k = s->ileave; k <= LB_N; k++) {
 				int k1 = indx2[k];
 				temp3 += s->ws[k1][ipntr] * s->wy[k1][jpntr];
@@ -647,18 +706,22 @@ SXS_HD int lb_formk(struct lb_state *s)
 	}
 	/* form the upper triangle of WN = [D+Y'ZZ'Y/theta   -L_a'+R_z' ; -L_a+R_z   S'AA'S*theta] */
 	const double theta = s->theta;
+	LB_NOUNROLL
 	for (int iy = 1; iy <= col; iy++) {
 		int is = col + iy;
 		int is1 = LB_M + iy;
+		LB_NOUNROLL
 		for (int jy = 1; jy <= iy; jy++) {
 			int js = col + jy;
 			int js1 = LB_M + jy;
 			wn[jy][iy] = wn1[iy][jy] / theta;
 			wn[js][is] = wn1[is1][js1] * theta;
 		}
+		LB_NOUNROLL
 		for (int jy = 1; jy <= iy - 1; jy++) {
 			wn[jy][is] = -wn1[is1][jy];
 		}
+		LB_NOUNROLL
 		for (int jy = iy; jy <= col; jy++) {
 			wn[jy][is] = wn1[is1][jy];
 		}
@@ -670,21 +733,27 @@ SXS_HD int lb_formk(struct lb_state *s)
 	}
 	/* then form L^-1(-L_a'+R_z') in the (1,2) block */
 	const int col2 = 2 * col;
+	LB_NOUNROLL
 	for (int js = col + 1; js <= col2; js++) {
 		/* column js of wn, rows 1..col, as the right-hand side of trans(T) x = b */
 		double b[LB_M + 1];
+		LB_NOUNROLL
 		for (int i = 1; i <= col; i++) {
 			b[i] = wn[i][js];
 		}
 		(void)lb_dtrsl_2m(wn, col, b, 11);
+		LB_NOUNROLL
 		for (int i = 1; i <= col; i++) {
 			wn[i][js] = b[i];
 		}
 	}
 	/* form S'AA'S*theta + (L^-1(-L_a'+R_z'))'(L^-1(-L_a'+R_z')) in the upper triangle of (2,2) */
+	LB_NOUNROLL
 	for (int is = col + 1; is <= col2; is++) {
+		LB_NOUNROLL
 		for (int js = is; js <= col2; js++) {
 			double dot = 0.0;
+			LB_NOUNROLL
 			for (int i = 1; i <= col; i++) {
 				dot += wn[i][is] * wn[i][js];
 			}
@@ -699,9 +768,10 @@ SXS_HD int lb_formk(struct lb_state *s)
 }
 
 /* r = -Z'B(xcp - xk) - Z'g (subalgorithms.c cmprlb, :1305-1391); the problem is always constrained. */
-SXS_HD int lb_cmprlb(struct lb_state *s)
+LB_FN int lb_cmprlb(struct lb_state *s)
 {
 	const int col = s->col;
+	LB_NOUNROLL
 	for (int i = 1; i <= s->nfree; i++) {
 		int k = s->index[i];
 		s->r[i] = -s->theta * (s->z[k] - s->x[k]) - s->g[k];
@@ -711,9 +781,11 @@ SXS_HD int lb_cmprlb(struct lb_state *s)
 		return -8;
 	}
 	int pointr = s->head;
+	LB_NOUNROLL
 	for (int j = 1; j <= col; j++) {
 		double a1 = s->wa[j];
 		double a2 = s->theta * s->wa[col + j];
+		LB_NOUNROLL
 		for (int i = 1; i <= s->nfree; i++) {
 			int k = s->index[i];
 			s->r[i] = s->r[i] + s->wy[k][pointr] * a1 + s->ws[k][pointr] * a2;
@@ -725,7 +797,7 @@ SXS_HD int lb_cmprlb(struct lb_state *s)
 
 /* Subspace minimisation with the 2011 projection/backtracking refinement
  * (subalgorithms.c subsm, :1903-2228).  On entry z holds the Cauchy point, r the reduced gradient. */
-SXS_HD int lb_subsm(struct lb_state *s)
+LB_FN int lb_subsm(struct lb_state *s)
 {
 	const int col = s->col, nsub = s->nfree;
 	const int *ind = s->index;
@@ -736,8 +808,10 @@ SXS_HD int lb_subsm(struct lb_state *s)
 	}
 	/* wv = W'Z d */
 	int pointr = s->head;
+	LB_NOUNROLL
 	for (int i = 1; i <= col; i++) {
 		double temp1 = 0.0, temp2 = 0.0;
+		LB_NOUNROLL
 		for (int j = 1; j <= nsub; j++) {
 			int k = ind[j];
 			temp1 += s->wy[k][pointr] * d[j];
@@ -754,6 +828,7 @@ SXS_HD int lb_subsm(struct lb_state *s)
 	if (info != 0) {
 		return info;
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= col; i++) {
 		wv[i] = -wv[i];
 	}
@@ -763,8 +838,10 @@ SXS_HD int lb_subsm(struct lb_state *s)
 	}
 	/* d = (1/theta) d + (1/theta^2) Z'W wv */
 	pointr = s->head;
+	LB_NOUNROLL
 	for (int jy = 1; jy <= col; jy++) {
 		int js = col + jy;
+		LB_NOUNROLL
 		for (int i = 1; i <= nsub; i++) {
 			int k = ind[i];
 			d[i] = d[i] + s->wy[k][pointr] * wv[jy] / theta + s->ws[k][pointr] * wv[js];
@@ -773,15 +850,18 @@ SXS_HD int lb_subsm(struct lb_state *s)
 	}
 	{
 		double inv = 1.0 / theta;
+		LB_NOUNROLL
 		for (int i = 1; i <= nsub; i++) {
 			d[i] = inv * d[i];
 		}
 	}
 	/* projected Newton step */
 	int iword = 0;
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		xp[i] = x[i];
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= nsub; i++) {
 		int k = ind[i];
 		double dk = d[i];
@@ -797,16 +877,19 @@ SXS_HD int lb_subsm(struct lb_state *s)
 	}
 	/* check sign of the directional derivative */
 	double dd_p = 0.0;
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		dd_p += (x[i] - s->x[i]) * s->g[i];
 	}
 	if (dd_p > 0.0) {
+		LB_NOUNROLL
 		for (int i = 1; i <= LB_N; i++) {
 			x[i] = xp[i];
 		}
 		double alpha = 1.0;
 		double temp1 = alpha;
 		int ibd = 0;
+		LB_NOUNROLL
 		for (int i = 1; i <= nsub; i++) {
 			int k = ind[i];
 			double dk = d[i];
@@ -841,6 +924,7 @@ SXS_HD int lb_subsm(struct lb_state *s)
 				d[ibd] = 0.0;
 			}
 		}
+		LB_NOUNROLL
 		for (int i = 1; i <= nsub; i++) {
 			int k = ind[i];
 			x[k] += alpha * d[i];
@@ -850,7 +934,7 @@ SXS_HD int lb_subsm(struct lb_state *s)
 }
 
 /* Store the newest correction pair and refresh S'S, S'Y (subalgorithms.c matupd, :1393-1511). */
-SXS_HD void lb_matupd(struct lb_state *s, double rr, double dr)
+LB_FN void lb_matupd(struct lb_state *s, double rr, double dr)
 {
 	if (s->iupdat <= LB_M) {
 		s->col = s->iupdat;
@@ -859,6 +943,7 @@ SXS_HD void lb_matupd(struct lb_state *s, double rr, double dr)
 		s->itail = s->itail % LB_M + 1;
 		s->head = s->head % LB_M + 1;
 	}
+	LB_NOUNROLL
 	for (int i = 1; i <= LB_N; i++) {
 		s->ws[i][s->itail] = s->d[i];
 		s->wy[i][s->itail] = s->r[i];
@@ -867,21 +952,27 @@ SXS_HD void lb_matupd(struct lb_state *s, double rr, double dr)
 	const int col = s->col;
 	if (s->iupdat > LB_M) {
 		/* move old information */
+		LB_NOUNROLL
 		for (int j = 1; j <= col - 1; j++) {
+			LB_NOUNROLL
 			for (int i = 0; i < j; i++) {
 				s->ss[1 + i][j] = s->ss[2 + i][j + 1];
 			}
+			LB_NOUNROLL
 			for (int i = 0; i < col - j; i++) {
 				s->sy[j + i][j] = s->sy[j + 1 + i][j + 1];
 			}
 		}
 	}
 	int pointr = s->head;
+	LB_NOUNROLL
 	for (int j = 1; j <= col - 1; j++) {
 		double a = 0.0, b = 0.0;
+		LB_NOUNROLL
 		for (int i = 1; i <= LB_N; i++) {
 			a += s->d[i] * s->wy[i][pointr];
 		}
+		LB_NOUNROLL
 		for (int i = 1; i <= LB_N; i++) {
 			b += s->ws[i][pointr] * s->d[i];
 		}
@@ -898,16 +989,20 @@ SXS_HD void lb_matupd(struct lb_state *s, double rr, double dr)
 }
 
 /* T = theta*S'S + L*D^-1*L', Cholesky-factored in place (subalgorithms.c formt, :920-974). */
-SXS_HD int lb_formt(struct lb_state *s)
+LB_FN int lb_formt(struct lb_state *s)
 {
 	const int col = s->col;
+	LB_NOUNROLL
 	for (int j = 1; j <= col; j++) {
 		s->wt[1][j] = s->theta * s->ss[1][j];
 	}
+	LB_NOUNROLL
 	for (int i = 2; i <= col; i++) {
+		LB_NOUNROLL
 		for (int j = i; j <= col; j++) {
 			int k1 = (i < j ? i : j) - 1;
 			double ddum = 0.0;
+			LB_NOUNROLL
 			for (int k = 1; k <= k1; k++) {
 				ddum += s->sy[i][k] * s->sy[j][k] / s->sy[k][k];
 			}
@@ -921,7 +1016,7 @@ SXS_HD int lb_formt(struct lb_state *s)
 }
 
 /* Safeguarded cubic/quadratic step of Moré & Thuente (linesearch.c dcstep, :485-763). */
-SXS_HD void lb_dcstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp,
+LB_FN void lb_dcstep(double *stx, double *fx, double *dx, double *sty, double *fy, double *dy, double *stp,
                       double fp, double dp, int *brackt, double stpmin, double stpmax)
 {
 	double gamma, p, q, r, s, sgnd, stpc, stpf, stpq, theta;
@@ -1043,7 +1138,7 @@ SXS_HD void lb_dcstep(double *stx, double *fx, double *dx, double *sty, double *
 /* One reverse-communication turn of the Moré–Thuente search (linesearch.c dcsrch, :161-483).
  * The stpmin = 0 / ftol / gtol / xtol argument checks of the START branch cannot fire with the
  * constants above and stp = 1 <= stpmax, gd < 0 (checked by the caller), so they are omitted. */
-SXS_HD void lb_dcsrch(struct lb_state *s, double f, double g, double *stp, double stpmax)
+LB_FN void lb_dcsrch(struct lb_state *s, double f, double g, double *stp, double stpmax)
 {
 	if (s->ls_task == LS_START) {
 		s->brackt = 0;
@@ -1126,219 +1221,287 @@ SXS_HD void lb_dcsrch(struct lb_state *s, double f, double g, double *stp, doubl
 	s->ls_task = LS_FG;
 }
 
-/* Objective callback: fills f and g[1..2] at x[1..2]. */
-#define LB_EVAL(CTX, S) sxs_fit_eval((CTX), (S)->x[1], (S)->x[2], &(S)->f, &(S)->g[1], &(S)->g[2])
+/* ---------------------------------------------------------------------------------------------
+ * Reverse-communication driver (lbfgsb.c mainlb, :327-1063, together with the driver loop of
+ * src/min_saxs.c:229-243).  lb_step() advances the optimiser until it needs the objective at
+ * s->x (returns LB_NEED_EVAL; the caller fills s->f, s->g[1..2] and calls again) or until it has
+ * terminated (returns LB_DONE; s->x, s->f hold what the reference's driver reads back, s->nfgv the
+ * number of objective evaluations).  Keeping the evaluation OUTSIDE the optimiser is what lets a
+ * GPU warp run 32 independent fits in lock-step: the optimiser logic diverges, the expensive
+ * objective is evaluated convergently by all lanes.
+ */
+enum lb_phase { LB_PH_INIT = 0, LB_PH_FIRST_EVAL, LB_PH_LINESEARCH, LB_PH_DONE };
+enum lb_status { LB_DONE = 0, LB_NEED_EVAL = 1 };
 
-/* Whole minimisation (lbfgsb.c mainlb, :327-1063, folded together with the reverse-communication
- * driver loop of src/min_saxs.c:229-243).  EVAL is a statement macro so the objective is inlined.
- * On return s->x, s->f hold what the reference's driver would read back; the number of objective
- * evaluations is s->nfgv. */
-#define LB_MINIMIZE(S, EVAL_STMT, FACTR, PGTOL)                                                        \
-	do {                                                                                              \
-		struct lb_state *s_ = (S);                                                                    \
-		lb_reset_memory(s_);                                                                          \
-		s_->iback = 0; s_->itail = 0; s_->nact = 0; s_->ileave = 0; s_->nenter = 0;                   \
-		s_->fold = 0.0; s_->dnorm = 0.0; s_->gd = 0.0; s_->stpmx = 0.0; s_->sbgnrm = 0.0;             \
-		s_->stp = 0.0; s_->gdold = 0.0; s_->dtd = 0.0; s_->iter = 0; s_->nfgv = 0; s_->nseg = 0;      \
-		s_->nfree = LB_N; s_->ifun = 0; s_->wrk = 0;                                                  \
-		s_->tol = (FACTR) * LB_EPSMCH;                                                                \
-		/* active(): project the start into the box, all variables boxed */                           \
-		for (int i_ = 1; i_ <= LB_N; i_++) {                                                          \
-			if (s_->x[i_] <= s_->l[i_]) {                                                             \
-				s_->x[i_] = s_->l[i_];                                                                \
-			} else if (s_->x[i_] >= s_->u[i_]) {                                                      \
-				s_->x[i_] = s_->u[i_];                                                                \
-			}                                                                                         \
-			s_->iwhere[i_] = (s_->u[i_] - s_->l[i_] <= 0.0) ? 3 : 0;                                  \
-		}                                                                                             \
-		EVAL_STMT;                                                                                    \
-		s_->nfgv = 1;                                                                                 \
-		s_->sbgnrm = lb_projgr(s_);                                                                   \
-		int done_ = (s_->sbgnrm <= (PGTOL));                                                          \
-		while (!done_) {                                                                              \
-			/* ---- generalised Cauchy point ---- */                                                  \
-			if (lb_cauchy(s_) != 0) {                                                                 \
-				lb_reset_memory(s_);                                                                  \
-				continue;                                                                             \
-			}                                                                                         \
-			lb_freev(s_);                                                                             \
-			s_->nact = LB_N - s_->nfree;                                                              \
-			/* ---- subspace minimisation ---- */                                                     \
-			if (s_->nfree != 0 && s_->col != 0) {                                                     \
-				int info_ = 0;                                                                        \
-				if (s_->wrk) {                                                                        \
-					info_ = lb_formk(s_);                                                             \
-				}                                                                                     \
-				if (info_ != 0) {                                                                     \
-					lb_reset_memory(s_);                                                              \
-					continue;                                                                         \
-				}                                                                                     \
-				info_ = lb_cmprlb(s_);                                                                \
-				if (info_ == 0) {                                                                     \
-					info_ = lb_subsm(s_);                                                             \
-				}                                                                                     \
-				if (info_ != 0) {                                                                     \
-					lb_reset_memory(s_);                                                              \
-					continue;                                                                         \
-				}                                                                                     \
-			}                                                                                         \
-			/* ---- line search along d = z - x (linesearch.c lnsrlb, :5-159) ---- */                 \
-			for (int i_ = 1; i_ <= LB_N; i_++) {                                                      \
-				s_->d[i_] = s_->z[i_] - s_->x[i_];                                                    \
-			}                                                                                         \
-			{                                                                                         \
-				double acc_ = 0.0;                                                                    \
-				for (int i_ = 1; i_ <= LB_N; i_++) {                                                  \
-					acc_ += s_->d[i_] * s_->d[i_];                                                    \
-				}                                                                                     \
-				s_->dtd = acc_;                                                                       \
-			}                                                                                         \
-			s_->dnorm = sqrt(s_->dtd);                                                                \
-			s_->stpmx = 1e10;                                                                         \
-			if (s_->iter == 0) {                                                                      \
-				s_->stpmx = 1.0;                                                                      \
-			} else {                                                                                  \
-				for (int i_ = 1; i_ <= LB_N; i_++) {                                                  \
-					double a1_ = s_->d[i_];                                                           \
-					if (a1_ < 0.0) {                                                                  \
-						double a2_ = s_->l[i_] - s_->x[i_];                                           \
-						if (a2_ >= 0.0) {                                                             \
-							s_->stpmx = 0.0;                                                          \
-						} else if (a1_ * s_->stpmx < a2_) {                                           \
-							s_->stpmx = a2_ / a1_;                                                    \
-						}                                                                             \
-					} else if (a1_ > 0.0) {                                                           \
-						double a2_ = s_->u[i_] - s_->x[i_];                                           \
-						if (a2_ <= 0.0) {                                                             \
-							s_->stpmx = 0.0;                                                          \
-						} else if (a1_ * s_->stpmx > a2_) {                                           \
-							s_->stpmx = a2_ / a1_;                                                    \
-						}                                                                             \
-					}                                                                                 \
-				}                                                                                     \
-			}                                                                                         \
-			s_->stp = 1.0;                                                                            \
-			for (int i_ = 1; i_ <= LB_N; i_++) {                                                      \
-				s_->t[i_] = s_->x[i_];                                                                \
-				s_->r[i_] = s_->g[i_];                                                                \
-			}                                                                                         \
-			s_->fold = s_->f;                                                                         \
-			s_->ifun = 0;                                                                             \
-			s_->iback = 0;                                                                            \
-			s_->ls_task = LS_START;                                                                   \
-			int info_ls_ = 0;                                                                         \
-			int restart_ = 0;                                                                         \
-			for (;;) {                                                                                \
-				{                                                                                     \
-					double acc_ = 0.0;                                                                \
-					for (int i_ = 1; i_ <= LB_N; i_++) {                                              \
-						acc_ += s_->g[i_] * s_->d[i_];                                                \
-					}                                                                                 \
-					s_->gd = acc_;                                                                    \
-				}                                                                                     \
-				int search_over_ = 0;                                                                 \
-				if (s_->ifun == 0) {                                                                  \
-					s_->gdold = s_->gd;                                                               \
-					if (s_->gd >= 0.0) {                                                              \
-						info_ls_ = -4; /* ascent direction in projection */                           \
-					}                                                                                 \
-				}                                                                                     \
-				if (info_ls_ == 0) {                                                                  \
-					lb_dcsrch(s_, s_->f, s_->gd, &s_->stp, s_->stpmx);                                \
-					if (s_->ls_task == LS_FG) {                                                       \
-						++s_->ifun;                                                                   \
-						++s_->nfgv;                                                                   \
-						s_->iback = s_->ifun - 1;                                                     \
-						if (s_->stp == 1.0) {                                                         \
-							for (int i_ = 1; i_ <= LB_N; i_++) {                                      \
-								s_->x[i_] = s_->z[i_];                                                \
-							}                                                                         \
-						} else {                                                                      \
-							for (int i_ = 1; i_ <= LB_N; i_++) {                                      \
-								s_->x[i_] = s_->stp * s_->d[i_] + s_->t[i_];                          \
-							}                                                                         \
-						}                                                                             \
-					} else {                                                                          \
-						search_over_ = 1;                                                             \
-					}                                                                                 \
-				}                                                                                     \
-				if (info_ls_ != 0 || s_->iback >= 20) {                                               \
-					/* restore the previous iterate */                                                \
-					for (int i_ = 1; i_ <= LB_N; i_++) {                                              \
-						s_->x[i_] = s_->t[i_];                                                        \
-						s_->g[i_] = s_->r[i_];                                                        \
-					}                                                                                 \
-					s_->f = s_->fold;                                                                 \
-					if (s_->col == 0) {                                                               \
-						/* abnormal termination in the line search */                                 \
-						if (info_ls_ == 0) {                                                          \
-							--s_->nfgv;                                                               \
-							--s_->ifun;                                                               \
-							--s_->iback;                                                              \
-						}                                                                             \
-						++s_->iter;                                                                   \
-						done_ = 1;                                                                    \
-					} else {                                                                          \
-						if (info_ls_ == 0) {                                                          \
-							--s_->nfgv;                                                               \
-						}                                                                             \
-						lb_reset_memory(s_);                                                          \
-						restart_ = 1;                                                                 \
-					}                                                                                 \
-					break;                                                                            \
-				}                                                                                     \
-				if (search_over_) {                                                                   \
-					break;                                                                            \
-				}                                                                                     \
-				EVAL_STMT;                                                                            \
-			}                                                                                         \
-			if (done_ || restart_) {                                                                  \
-				continue;                                                                             \
-			}                                                                                         \
-			/* ---- new iterate accepted ---- */                                                      \
-			++s_->iter;                                                                               \
-			s_->sbgnrm = lb_projgr(s_);                                                               \
-			if (s_->sbgnrm <= (PGTOL)) {                                                              \
-				done_ = 1;                                                                            \
-				continue;                                                                             \
-			}                                                                                         \
-			{                                                                                         \
-				double ddum_ = lb_max(lb_max(lb_abs(s_->fold), lb_abs(s_->f)), 1.0);                  \
-				if (s_->fold - s_->f <= s_->tol * ddum_) {                                            \
-					done_ = 1;                                                                        \
-					continue;                                                                         \
-				}                                                                                     \
-			}                                                                                         \
-			/* ---- BFGS update ---- */                                                               \
-			for (int i_ = 1; i_ <= LB_N; i_++) {                                                      \
-				s_->r[i_] = s_->g[i_] - s_->r[i_];                                                    \
-			}                                                                                         \
-			double rr_ = 0.0;                                                                         \
-			for (int i_ = 1; i_ <= LB_N; i_++) {                                                      \
-				rr_ += s_->r[i_] * s_->r[i_];                                                         \
-			}                                                                                         \
-			double dr_, ddum2_;                                                                       \
-			if (s_->stp == 1.0) {                                                                     \
-				dr_ = s_->gd - s_->gdold;                                                             \
-				ddum2_ = -s_->gdold;                                                                  \
-			} else {                                                                                  \
-				dr_ = (s_->gd - s_->gdold) * s_->stp;                                                 \
-				for (int i_ = 1; i_ <= LB_N; i_++) {                                                  \
-					s_->d[i_] = s_->stp * s_->d[i_];                                                  \
-				}                                                                                     \
-				ddum2_ = -s_->gdold * s_->stp;                                                        \
-			}                                                                                         \
-			if (dr_ <= LB_EPSMCH * ddum2_) {                                                          \
-				s_->updatd = 0; /* skip the update */                                                 \
-				continue;                                                                             \
-			}                                                                                         \
-			s_->updatd = 1;                                                                           \
-			++s_->iupdat;                                                                             \
-			lb_matupd(s_, rr_, dr_);                                                                  \
-			if (lb_formt(s_) != 0) {                                                                  \
-				lb_reset_memory(s_);                                                                  \
-			}                                                                                         \
-		}                                                                                             \
-	} while (0)
+LB_FN void lb_begin(struct lb_state *s, double x1, double x2, double l1, double u1, double l2, double u2, double factr)
+{
+	s->x[1] = x1; s->x[2] = x2;
+	s->l[1] = l1; s->l[2] = l2;
+	s->u[1] = u1; s->u[2] = u2;
+	s->g[1] = 0.0; s->g[2] = 0.0;
+	s->f = 0.0;
+	/* the reference zeroes its whole workspace before every fit (src/min_saxs.c:217-221) */
+	LB_NOUNROLL
+	for (int i = 0; i <= LB_N; i++) {
+		LB_NOUNROLL
+		for (int j = 0; j <= LB_M; j++) { s->ws[i][j] = 0.0; s->wy[i][j] = 0.0; }
+		s->z[i] = s->r[i] = s->d[i] = s->t[i] = s->xp[i] = 0.0;
+		s->index[i] = s->iwhere[i] = s->indx2[i] = 0;
+	}
+	LB_NOUNROLL
+	for (int i = 0; i <= LB_M; i++) {
+		LB_NOUNROLL
+		for (int j = 0; j <= LB_M; j++) { s->sy[i][j] = 0.0; s->ss[i][j] = 0.0; s->wt[i][j] = 0.0; }
+	}
+	LB_NOUNROLL
+	for (int i = 0; i <= LB_M2; i++) {
+		LB_NOUNROLL
+		for (int j = 0; j <= LB_M2; j++) { s->wn[i][j] = 0.0; s->wn1[i][j] = 0.0; }
+	}
+	LB_NOUNROLL
+	for (int i = 0; i <= 8 * LB_M; i++) { s->wa[i] = 0.0; }
+	s->brackt = 0; s->stage = 0; s->ls_task = LS_START;
+	s->ginit = s->gtest = s->gx = s->gy = s->finit = s->fx = s->fy = 0.0;
+	s->stx = s->sty = s->stmin = s->stmax = s->width = s->width1 = 0.0;
+
+	lb_reset_memory(s);
+	s->iback = 0; s->itail = 0; s->nact = 0; s->ileave = 0; s->nenter = 0;
+	s->fold = 0.0; s->dnorm = 0.0; s->gd = 0.0; s->stpmx = 0.0; s->sbgnrm = 0.0;
+	s->stp = 0.0; s->gdold = 0.0; s->dtd = 0.0; s->iter = 0; s->nfgv = 0; s->nseg = 0;
+	s->nfree = LB_N; s->ifun = 0; s->wrk = 0;
+	s->tol = factr * LB_EPSMCH;
+	s->phase = LB_PH_INIT;
+}
+
+LB_FN int lb_step(struct lb_state *s, const double pgtol)
+{
+	int info_ls;
+
+	if (s->phase == LB_PH_LINESEARCH) {
+		goto after_linesearch_eval;
+	}
+	if (s->phase == LB_PH_FIRST_EVAL) {
+		goto after_first_eval;
+	}
+	if (s->phase == LB_PH_DONE) {
+		return LB_DONE;
+	}
+
+	/* active(): project the start into the box, all variables boxed (subalgorithms.c:7-118) */
+	LB_NOUNROLL
+	for (int i = 1; i <= LB_N; i++) {
+		if (s->x[i] <= s->l[i]) {
+			s->x[i] = s->l[i];
+		} else if (s->x[i] >= s->u[i]) {
+			s->x[i] = s->u[i];
+		}
+		s->iwhere[i] = (s->u[i] - s->l[i] <= 0.0) ? 3 : 0;
+	}
+	s->phase = LB_PH_FIRST_EVAL;
+	return LB_NEED_EVAL;
+
+after_first_eval:
+	s->nfgv = 1;
+	s->sbgnrm = lb_projgr(s);
+	if (s->sbgnrm <= pgtol) {
+		goto finished;
+	}
+
+new_iteration: /* label 222 of mainlb */
+	/* ---- generalised Cauchy point ---- */
+	if (lb_cauchy(s) != 0) {
+		lb_reset_memory(s);
+		goto new_iteration;
+	}
+	lb_freev(s);
+	s->nact = LB_N - s->nfree;
+	/* ---- subspace minimisation ---- */
+	if (s->nfree != 0 && s->col != 0) {
+		int info = 0;
+		if (s->wrk) {
+			info = lb_formk(s);
+		}
+		if (info != 0) {
+			lb_reset_memory(s);
+			goto new_iteration;
+		}
+		info = lb_cmprlb(s);
+		if (info == 0) {
+			info = lb_subsm(s);
+		}
+		if (info != 0) {
+			lb_reset_memory(s);
+			goto new_iteration;
+		}
+	}
+	/* ---- line search along d = z - x (linesearch.c lnsrlb, :5-159) ---- */
+	LB_NOUNROLL
+	for (int i = 1; i <= LB_N; i++) {
+		s->d[i] = s->z[i] - s->x[i];
+	}
+	{
+		double acc = 0.0;
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			acc += s->d[i] * s->d[i];
+		}
+		s->dtd = acc;
+	}
+	s->dnorm = sqrt(s->dtd);
+	s->stpmx = 1e10;
+	if (s->iter == 0) {
+		s->stpmx = 1.0;
+	} else {
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			const double a1 = s->d[i];
+			if (a1 < 0.0) {
+				const double a2 = s->l[i] - s->x[i];
+				if (a2 >= 0.0) {
+					s->stpmx = 0.0;
+				} else if (a1 * s->stpmx < a2) {
+					s->stpmx = a2 / a1;
+				}
+			} else if (a1 > 0.0) {
+				const double a2 = s->u[i] - s->x[i];
+				if (a2 <= 0.0) {
+					s->stpmx = 0.0;
+				} else if (a1 * s->stpmx > a2) {
+					s->stpmx = a2 / a1;
+				}
+			}
+		}
+	}
+	s->stp = 1.0;
+	LB_NOUNROLL
+	for (int i = 1; i <= LB_N; i++) {
+		s->t[i] = s->x[i];
+		s->r[i] = s->g[i];
+	}
+	s->fold = s->f;
+	s->ifun = 0;
+	s->iback = 0;
+	s->ls_task = LS_START;
+
+after_linesearch_eval: /* label 666/556: one turn of the search with f, g at the current x */
+	info_ls = 0;
+	{
+		double acc = 0.0;
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			acc += s->g[i] * s->d[i];
+		}
+		s->gd = acc;
+	}
+	{
+		int search_over = 0;
+		if (s->ifun == 0) {
+			s->gdold = s->gd;
+			if (s->gd >= 0.0) {
+				info_ls = -4; /* ascent direction in projection */
+			}
+		}
+		if (info_ls == 0) {
+			lb_dcsrch(s, s->f, s->gd, &s->stp, s->stpmx);
+			if (s->ls_task == LS_FG) {
+				++s->ifun;
+				++s->nfgv;
+				s->iback = s->ifun - 1;
+				if (s->stp == 1.0) {
+					LB_NOUNROLL
+					for (int i = 1; i <= LB_N; i++) {
+						s->x[i] = s->z[i];
+					}
+				} else {
+					LB_NOUNROLL
+					for (int i = 1; i <= LB_N; i++) {
+						s->x[i] = s->stp * s->d[i] + s->t[i];
+					}
+				}
+			} else {
+				search_over = 1;
+			}
+		}
+		if (info_ls != 0 || s->iback >= 20) {
+			/* restore the previous iterate */
+			LB_NOUNROLL
+			for (int i = 1; i <= LB_N; i++) {
+				s->x[i] = s->t[i];
+				s->g[i] = s->r[i];
+			}
+			s->f = s->fold;
+			if (s->col == 0) {
+				/* abnormal termination in the line search */
+				if (info_ls == 0) {
+					--s->nfgv;
+					--s->ifun;
+					--s->iback;
+				}
+				++s->iter;
+				goto finished;
+			}
+			if (info_ls == 0) {
+				--s->nfgv;
+			}
+			lb_reset_memory(s);
+			goto new_iteration;
+		}
+		if (!search_over) {
+			s->phase = LB_PH_LINESEARCH;
+			return LB_NEED_EVAL;
+		}
+	}
+	/* ---- new iterate accepted (label 777) ---- */
+	++s->iter;
+	s->sbgnrm = lb_projgr(s);
+	if (s->sbgnrm <= pgtol) {
+		goto finished;
+	}
+	{
+		const double ddum = lb_max(lb_max(lb_abs(s->fold), lb_abs(s->f)), 1.0);
+		if (s->fold - s->f <= s->tol * ddum) {
+			goto finished;
+		}
+	}
+	/* ---- BFGS update ---- */
+	LB_NOUNROLL
+	for (int i = 1; i <= LB_N; i++) {
+		s->r[i] = s->g[i] - s->r[i];
+	}
+	{
+		double rr = 0.0;
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			rr += s->r[i] * s->r[i];
+		}
+		double dr, ddum2;
+		if (s->stp == 1.0) {
+			dr = s->gd - s->gdold;
+			ddum2 = -s->gdold;
+		} else {
+			dr = (s->gd - s->gdold) * s->stp;
+			LB_NOUNROLL
+			for (int i = 1; i <= LB_N; i++) {
+				s->d[i] = s->stp * s->d[i];
+			}
+			ddum2 = -s->gdold * s->stp;
+		}
+		if (dr <= LB_EPSMCH * ddum2) {
+			s->updatd = 0; /* skip the update */
+			goto new_iteration;
+		}
+		s->updatd = 1;
+		++s->iupdat;
+		lb_matupd(s, rr, dr);
+		if (lb_formt(s) != 0) {
+			lb_reset_memory(s);
+		}
+	}
+	goto new_iteration;
+
+finished:
+	s->phase = LB_PH_DONE;
+	return LB_DONE;
+}
 
 #endif /* SXS_LBFGSB_N2M3_H */

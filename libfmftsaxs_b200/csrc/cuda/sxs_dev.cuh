@@ -35,9 +35,10 @@ __host__ __device__ inline int sxs_ml_index(int L, int m, int l) { return m * (L
 
 /* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
 
-/* K4: one fit per point.  x: cross terms, x[(q*6 + k)*stride + p]; res[p*4] = chi, c1, c2, evaluations. */
-int sxs_launch_fit(const double *d_x, long long stride, long long npts, const double *d_a, const double *d_qvals,
-                   int qnum, double mult, double peak, int rescale, double *d_res, cudaStream_t stream);
+/* K4: one fit per point.  x: point-major cross terms, x[p*6*qnum + q*6 + k]; res[p*4] = chi, c1, c2,
+ * evaluations.  d_ticket: one device word used as the work queue head (reset by the launcher). */
+int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const double *d_qvals, int qnum, double mult,
+                   double peak, int rescale, double *d_res, unsigned long long *d_ticket, cudaStream_t stream);
 
 /* Self terms of the pair (A, B) in comp_const_int order (src/fftsaxs.c:27-50,638-643); out[k*qnum + q],
  * VD/VW/DW already doubled as fill_const applies them (src/fftsaxs.c:76-81). */

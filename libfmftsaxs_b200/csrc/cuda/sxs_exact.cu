@@ -16,13 +16,24 @@
 #include "sxs_dev.cuh"
 
 #define SXS_HD __host__ __device__ __forceinline__
+#define SXS_ROWMAJOR_VEC 1
 #include "fit_point.h"
 
 #define SXS_FIT_MAXQ 512
+#define SXS_FIT_THREADS 128
 
-__global__ void __launch_bounds__(128)
-k_fit(const double *__restrict__ x, long long stride, long long npts, const double *__restrict__ a,
-      const double *__restrict__ qvals, int qnum, double mult, double peak, int rescale, double *__restrict__ res)
+/* K4.  X is point-major: the 6*qnum cross terms of point p are the contiguous row X[p*6*qnum + q*6 + k]
+ * (2.4 KB at Q = 50), read with 16-byte loads.
+ *
+ * Every lane owns one fit at a time and runs the reverse-communication optimiser lb_step() until it asks
+ * for the objective; then the whole warp evaluates the objective together.  The optimiser logic is
+ * branchy and diverges between lanes, the objective (2 passes over q with an exp each, ~95 % of the
+ * arithmetic) is executed convergently.  A lane whose fit has terminated takes the next point from a
+ * global ticket counter at the top of the next round, so lanes do not idle while a neighbour finishes a
+ * long line search (evaluations per fit range from 2 to ~50). */
+__global__ void __launch_bounds__(SXS_FIT_THREADS)
+k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
+      int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {
 	extern __shared__ double s_tab[]; /* [6*qnum] moments, then [qnum] q grid */
 	double *s_a = s_tab;
@@ -35,31 +46,50 @@ k_fit(const double *__restrict__ x, long long stride, long long npts, const doub
 	}
 	__syncthreads();
 
-	const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= npts) {
-		return;
+	struct lb_state st;
+	struct sxs_fit_ctx ctx;
+	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
+	ctx.x = X; ctx.scale = 1.0;
+	long long p = -1;
+	bool have = false, drained = false;
+
+	for (;;) {
+		if (!have && !drained) {
+			p = (long long)atomicAdd(ticket, 1ull);
+			if (p < npts) {
+				ctx.x = X + (size_t)p * 6 * qnum;
+				ctx.scale = 1.0;
+				if (rescale) {
+					ctx.scale = sxs_fit_rescale(&ctx, peak);
+				}
+				lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
+				have = true;
+			} else {
+				drained = true;
+			}
+		}
+		if (__ballot_sync(0xffffffffu, have) == 0u) {
+			break;
+		}
+		if (have) {
+			if (lb_step(&st, 1e-5) == LB_DONE) {
+				res[p * 4 + 0] = sqrt(st.f);
+				res[p * 4 + 1] = st.x[1];
+				res[p * 4 + 2] = st.x[2];
+				res[p * 4 + 3] = (double)st.nfgv;
+				have = false;
+			}
+		}
+		__syncwarp();
+		if (have) {
+			sxs_fit_eval(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+		}
+		__syncwarp();
 	}
-	double score, c1, c2;
-	int nfg;
-	if (rescale) {
-		sxs_fit_point(x + p, stride, s_a, s_q, qnum, mult, peak, &score, &c1, &c2, &nfg);
-	} else {
-		/* sxs_lbfgs_fitting on cross terms as given: a unit rescale factor */
-		struct sxs_fit_ctx ctx;
-		ctx.x = x + p; ctx.stride = stride; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
-		const double i0 = ctx.x[0 * stride] + ctx.x[3 * stride] + ctx.x[5 * stride] + ctx.x[2 * stride] -
-		                  ctx.x[1 * stride] - ctx.x[4 * stride];
-		/* peak := I(0) makes scale exactly 1.0 */
-		sxs_fit_point(x + p, stride, s_a, s_q, qnum, mult, i0, &score, &c1, &c2, &nfg);
-	}
-	res[p * 4 + 0] = score;
-	res[p * 4 + 1] = c1;
-	res[p * 4 + 2] = c2;
-	res[p * 4 + 3] = (double)nfg;
 }
 
-int sxs_launch_fit(const double *d_x, long long stride, long long npts, const double *d_a, const double *d_qvals,
-                   int qnum, double mult, double peak, int rescale, double *d_res, cudaStream_t stream)
+int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const double *d_qvals, int qnum, double mult,
+                   double peak, int rescale, double *d_res, unsigned long long *d_ticket, cudaStream_t stream)
 {
 	if (npts <= 0) {
 		return 0;
@@ -68,23 +98,29 @@ int sxs_launch_fit(const double *d_x, long long stride, long long npts, const do
 		sxs_cuda_set_error("qnum %d exceeds %d", qnum, SXS_FIT_MAXQ);
 		return -1;
 	}
-	const int threads = 128;
-	const long long blocks = (npts + threads - 1) / threads;
-	k_fit<<<(unsigned)blocks, threads, sizeof(double) * 7 * qnum, stream>>>(d_x, stride, npts, d_a, d_qvals, qnum,
-	                                                                         mult, peak, rescale, d_res);
+	int dev = 0, sms = 148, per_sm = 4;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t shm = sizeof(double) * 7 * qnum;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
+	if (per_sm < 1) per_sm = 1;
+	long long blocks = (long long)sms * per_sm;
+	const long long need = (npts + SXS_FIT_THREADS - 1) / SXS_FIT_THREADS;
+	if (blocks > need) blocks = need;
+	SXS_CK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), stream));
+	k_fit<<<(unsigned)blocks, SXS_FIT_THREADS, shm, stream>>>(d_x, npts, d_a, d_qvals, qnum, mult, peak, rescale, d_res, d_ticket);
 	SXS_CK_LAUNCH();
 	return 0;
 }
 
-/* cross[(p*6 + k)*qnum + q]  ->  x[(q*6 + k)*npts + p] */
-__global__ void k_cross_to_strided(const double *__restrict__ cross, long long npts, int qnum, double *__restrict__ x)
+/* cross[(p*6 + k)*qnum + q]  ->  X[p*6*qnum + q*6 + k] */
+__global__ void k_cross_to_rows(const double *__restrict__ cross, long long npts, int qnum, double *__restrict__ x)
 {
 	const long long total = npts * 6 * qnum;
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-		const long long p = i % npts;
-		const long long qk = i / npts;
-		const int k = (int)(qk % 6);
-		const int q = (int)(qk / 6);
+		const long long p = i / (6 * qnum);
+		const int r = (int)(i % (6 * qnum));
+		const int q = r / 6, k = r % 6;
 		x[i] = cross[(p * 6 + k) * qnum + q];
 	}
 }
@@ -97,22 +133,24 @@ extern "C" int sxs_cuda_fit_profiles(int device, const double *cross, long long 
 	}
 	SXS_CK(cudaSetDevice(device));
 	double *d_cross = NULL, *d_x = NULL, *d_a = NULL, *d_q = NULL, *d_res = NULL;
+	unsigned long long *d_ticket = NULL;
 	const size_t nx = (size_t)npts * 6 * qnum;
 	SXS_CK(cudaMalloc(&d_cross, sizeof(double) * nx));
 	SXS_CK(cudaMalloc(&d_x, sizeof(double) * nx));
 	SXS_CK(cudaMalloc(&d_a, sizeof(double) * 6 * qnum));
 	SXS_CK(cudaMalloc(&d_q, sizeof(double) * qnum));
 	SXS_CK(cudaMalloc(&d_res, sizeof(double) * 4 * npts));
+	SXS_CK(cudaMalloc(&d_ticket, sizeof(unsigned long long)));
 	SXS_CK(cudaMemcpy(d_cross, cross, sizeof(double) * nx, cudaMemcpyHostToDevice));
 	SXS_CK(cudaMemcpy(d_a, a, sizeof(double) * 6 * qnum, cudaMemcpyHostToDevice));
 	SXS_CK(cudaMemcpy(d_q, qvals, sizeof(double) * qnum, cudaMemcpyHostToDevice));
-	k_cross_to_strided<<<1184, 256>>>(d_cross, npts, qnum, d_x);
+	k_cross_to_rows<<<1184, 256>>>(d_cross, npts, qnum, d_x);
 	SXS_CK_LAUNCH();
-	int rc = sxs_launch_fit(d_x, npts, npts, d_a, d_q, qnum, mult, peak, rescale, d_res, 0);
+	int rc = sxs_launch_fit(d_x, npts, d_a, d_q, qnum, mult, peak, rescale, d_res, d_ticket, 0);
 	if (rc == 0) {
 		SXS_CK(cudaMemcpy(out, d_res, sizeof(double) * 4 * npts, cudaMemcpyDeviceToHost));
 	}
-	cudaFree(d_cross); cudaFree(d_x); cudaFree(d_a); cudaFree(d_q); cudaFree(d_res);
+	cudaFree(d_cross); cudaFree(d_x); cudaFree(d_a); cudaFree(d_q); cudaFree(d_res); cudaFree(d_ticket);
 	return rc;
 }
 
@@ -124,8 +162,9 @@ __global__ void k_fit_eval(const double *__restrict__ cross, const double *__res
 		return;
 	}
 	struct sxs_fit_ctx ctx;
-	ctx.x = cross; /* cross[k*qnum + q]: element (q,k) at (q*6+k)*stride needs a transposed view */
+	ctx.x = cross; /* point-major row x[q*6 + k] */
 	ctx.stride = 1;
+	ctx.qstride = 6;
 	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0;
 	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
 	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);

@@ -84,7 +84,8 @@ struct sxs_cuda_plan {
 	/* workspace (grow-only) */
 	double2 *d_T;  size_t cap_T;   /* [zg][q][m][l][l1] */
 	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g] */
-	double *d_X;   size_t cap_X;   /* [q][6][chunk] */
+	double *d_X;   size_t cap_X;   /* [chunk][q][6] point-major rows */
+	unsigned long long *d_ticket;
 	double *d_res; size_t cap_res; /* [points][4] */
 	unsigned long long *d_keys, *d_keys_sorted, *d_pkeys;
 	unsigned int *d_rows, *d_rows_sorted, *d_pid;
@@ -202,6 +203,7 @@ extern "C" sxs_cuda_plan *sxs_cuda_plan_create(int device, int L, int qnum, cons
 	PC(cudaMalloc(&p->d_At, sizeof(double2) * nrot));
 	PC(cudaMalloc(&p->d_Bt, sizeof(double2) * nrot));
 	PC(cudaMalloc(&p->d_a, sizeof(double) * 6 * qnum));
+	PC(cudaMalloc(&p->d_ticket, sizeof(unsigned long long)));
 	PC(cudaMemcpy(p->d_qvals, qvals, sizeof(double) * qnum, cudaMemcpyHostToDevice));
 	PC(cudaMemcpy(p->d_dsymb, dsymb, sizeof(double) * nds, cudaMemcpyHostToDevice));
 	PC(cudaMemcpy(p->d_dwig, dwig, sizeof(double) * ndw, cudaMemcpyHostToDevice));
@@ -227,7 +229,7 @@ extern "C" void sxs_cuda_plan_destroy(sxs_cuda_plan *p)
 	void *ptrs[] = {p->d_qvals, p->d_dsymb, p->d_dwig, p->d_tw, p->d_coefA, p->d_coefB, p->d_const, p->d_At, p->d_Bt,
 	                p->d_a, p->d_bessel, p->d_T, p->d_St, p->d_X, p->d_res, p->d_keys, p->d_keys_sorted, p->d_pkeys,
 	                p->d_rows, p->d_rows_sorted, p->d_pid, p->d_cub, p->d_zoff, p->d_slab_flag, p->d_index_in,
-	                p->d_out3};
+	                p->d_out3, p->d_ticket};
 	for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) {
 		if (ptrs[i] != NULL) {
 			cudaFree(ptrs[i]);
@@ -510,11 +512,12 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
  * (z, b2, b1, g1, g2, a2) order, so a block mostly works inside one cell: the receptor rows it reads
  * differ only in g1 (nearly warp-uniform) and the ligand rows only in g2 — both 16-byte elements of the
  * same 496-byte row, served by L1/L2.
- * X[(q*6 + k)*xstride + (p - p0)] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108). */
+ * X[(p - p0)*6*qnum + q*6 + k] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108);
+ * point-major rows, so that K4 streams one contiguous 6*qnum row per fit. */
 __global__ void __launch_bounds__(256)
 k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0,
         const double2 *__restrict__ At, const double2 *__restrict__ St, const double2 *__restrict__ tw,
-        const double *__restrict__ cst, double *__restrict__ X, long long xstride)
+        const double *__restrict__ cst, double *__restrict__ X)
 {
 	extern __shared__ double2 s_tw[];
 	const int N = 2 * L + 1, nb = L + 1, ML = sxs_ml_count(L);
@@ -568,14 +571,10 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 			ka -= N;
 		}
 	}
-	const long long col = p - p0;
-	double *xo = X + (size_t)q * 6 * xstride + col;
-	xo[0 * xstride] = cst[0 * qnum + q] + 2.0 * f0;
-	xo[1 * xstride] = cst[1 * qnum + q] + 2.0 * f1;
-	xo[2 * xstride] = cst[2 * qnum + q] + 2.0 * f2;
-	xo[3 * xstride] = cst[3 * qnum + q] + 2.0 * f3;
-	xo[4 * xstride] = cst[4 * qnum + q] + 2.0 * f4;
-	xo[5 * xstride] = cst[5 * qnum + q] + 2.0 * f5;
+	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - p0) * qnum + q) * 6);
+	xo[0] = make_double2(cst[0 * qnum + q] + 2.0 * f0, cst[1 * qnum + q] + 2.0 * f1);
+	xo[1] = make_double2(cst[2 * qnum + q] + 2.0 * f2, cst[3 * qnum + q] + 2.0 * f3);
+	xo[2] = make_double2(cst[4 * qnum + q] + 2.0 * f4, cst[5 * qnum + q] + 2.0 * f5);
 }
 
 /* ---------------------------------------------------------------- scatter */
@@ -613,7 +612,7 @@ __global__ void k_gather_sorted(const unsigned int *__restrict__ pid_incl, long 
 /* cross terms of sorted rows back to list order (stage access for the parity tests) */
 __global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, const unsigned int *__restrict__ pid_incl,
                                long long nvalid, long long p0, long long p1, const double *__restrict__ X,
-                               long long xstride, int qnum, double *__restrict__ cross)
+                               int qnum, double *__restrict__ cross)
 {
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nvalid) {
@@ -626,7 +625,7 @@ __global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, con
 	const unsigned int row = rows_sorted[i];
 	for (int q = 0; q < qnum; q++) {
 		for (int k = 0; k < 6; k++) {
-			cross[((size_t)row * 6 + k) * qnum + q] = X[((size_t)q * 6 + k) * xstride + (p - p0)];
+			cross[((size_t)row * 6 + k) * qnum + q] = X[((size_t)(p - p0) * qnum + q) * 6 + k];
 		}
 	}
 }
@@ -863,16 +862,16 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 			dim3 grid((unsigned)((cnt + 255) / 256), Q);
 			timer_begin(p, 2, st);
 			k_cross<<<grid, 256, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, z_first, p->d_At, p->d_St, p->d_tw,
-			                                                 p->d_const, p->d_X, cnt);
+			                                                 p->d_const, p->d_X);
 			SXS_CK_LAUNCH(); launches++;
 			timer_end(p, 2, st);
 			if (d_cross_out != NULL) {
 				k_gather_cross<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_rows_sorted, p->d_pid, nvalid, c0, c1e,
-				                                                              p->d_X, cnt, Q, d_cross_out);
+				                                                              p->d_X, Q, d_cross_out);
 				SXS_CK_LAUNCH(); launches++;
 			}
 			timer_begin(p, 3, st);
-			if (sxs_launch_fit(p->d_X, cnt, cnt, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)c0 * 4, st) != 0) {
+			if (sxs_launch_fit(p->d_X, cnt, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)c0 * 4, p->d_ticket, st) != 0) {
 				free(h_zlist);
 				return -1;
 			}
@@ -992,6 +991,37 @@ extern "C" int sxs_cuda_plan_cross_terms_i32(sxs_cuda_plan *p, const int *index,
 	cudaFree(d_idx);
 	cudaFree(d_cross);
 	return rc;
+}
+
+/* histogram of objective evaluations per fit over the points of the last score call (bin 63 = 63 or more) */
+__global__ void k_nfg_hist(const double *__restrict__ res, long long np, unsigned long long *__restrict__ hist)
+{
+	const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= np) {
+		return;
+	}
+	int n = (int)res[p * 4 + 3];
+	if (n > 63) n = 63;
+	if (n < 0) n = 0;
+	atomicAdd(&hist[n], 1ull);
+}
+
+extern "C" int sxs_cuda_plan_fit_evaluations(sxs_cuda_plan *p, long long *hist64)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	const long long np = p->stats[0];
+	memset(hist64, 0, sizeof(long long) * 64);
+	if (np <= 0 || p->d_res == NULL) {
+		return 0;
+	}
+	unsigned long long *d_h = NULL;
+	SXS_CK(cudaMalloc(&d_h, sizeof(unsigned long long) * 64));
+	SXS_CK(cudaMemset(d_h, 0, sizeof(unsigned long long) * 64));
+	k_nfg_hist<<<(unsigned)((np + 255) / 256), 256>>>(p->d_res, np, d_h);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaMemcpy(hist64, d_h, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
+	cudaFree(d_h);
+	return 0;
 }
 
 /* ------------------------------------------------------------ calibration */

@@ -7,14 +7,14 @@ void cpu_fit_points(const double *x, int npts, const double *a, const double *qv
                     double peak, double *out)
 {
 	for (int p = 0; p < npts; p++) {
-		/* re-pack to the strided device layout x[(q*6+c)*stride] with stride 1 */
+		/* re-pack to the point-major device row x[q*6 + c] */
 		double buf[6 * 512];
 		for (int c = 0; c < 6; c++)
 			for (int q = 0; q < qnum; q++)
 				buf[q * 6 + c] = x[((long)p * 6 + c) * qnum + q];
 		double s, c1, c2;
 		int nfg;
-		sxs_fit_point(buf, 1, a, qvals, qnum, mult, peak, &s, &c1, &c2, &nfg);
+		sxs_fit_point(buf, 1, 6, a, qvals, qnum, mult, peak, &s, &c1, &c2, &nfg);
 		out[4 * p] = s; out[4 * p + 1] = c1; out[4 * p + 2] = c2; out[4 * p + 3] = nfg;
 	}
 }
