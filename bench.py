@@ -94,8 +94,10 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- workload
 
-def build_inputs(expand, opt_params, seed_rank, nrot, nz):
-    """molecules identical on every rank, pose list seeded per rank"""
+def build_inputs(expand, opt_params, native_cross, seed_rank, nrot, nz):
+    """molecules identical on every rank, pose list seeded per rank.  The "experimental" curve is the computed
+    profile of pose 0 of rank 0's list at c1 = c2 = 1 with 5 % errors — like examples/run_correlate.sh, which
+    scores against the single_saxs profile of a reference complex."""
     from libfmftsaxs_b200 import workload as wl
     w = wl.make(WORKLOAD, nrot=nrot, nz=nz)
     if seed_rank:
@@ -106,7 +108,10 @@ def build_inputs(expand, opt_params, seed_rank, nrot, nz):
                            sa=w["rec"]["sa"], water_mode=1)
     coefB, rmB, _ = expand(wl.MAP_PATH, w["lig"]["xyz"], w["lig"]["res"], w["lig"]["atm"], w["lig"]["radius"], q, L,
                            sa=w["lig"]["sa"], water_mode=1)
-    eq, ei, ee = wl.experimental_curve(coefA, coefB, q)
+    native_idx = wl.make_pose_indices(w["L"], w["zvals"][:1] * 0 + 40.0, 1, w["seed"] + 77)  # one pose at z = 40
+    X0 = native_cross(native_idx, coefA, coefB, q, [40.0], L)[0]   # [6][Q]: VV,VD,VW,DD,DW,WW
+    I0 = X0[0] - X0[1] + X0[2] + X0[3] - X0[4] + X0[5]              # c1 = c2 = 1 -> G = 1
+    eq, ei, ee = q.copy(), I0, 0.05 * I0
     a, scal = opt_params(eq, ei, ee, q, wl.mean_radius(w["rec"], w["lig"]))
     w.update(coefA=coefA, coefB=coefB, a=a, scal=scal)
     return w
@@ -144,7 +149,14 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsxsref.so missing (built from /root/reference by oracle/Makefile)"}))
         return 0
     from multiprocessing import Pool
-    w = build_inputs(refso.expand, refso.opt_params, 0, args.nrot, args.nz)
+    from golden import proto_cross_terms as proto
+
+    def native_cross(idx, coefA, coefB, q, zv, L):
+        A = coefA[..., 0] + 1j * coefA[..., 1]
+        B = coefB[..., 0] + 1j * coefB[..., 1]
+        return proto.cross_terms(idx, A, B, q, zv, L, proto.reference_tables(L, q, zv))
+
+    w = build_inputs(refso.expand, refso.opt_params, native_cross, 0, args.nrot, args.nz)
     L = w["L"]
     N = 2 * L + 1
     cores = os.cpu_count() or 1
@@ -195,7 +207,16 @@ def run_product(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    w = build_inputs(capi.expand, capi.opt_params, rank, args.nrot, args.nz)
+    def native_cross(idx, coefA, coefB, q, zv, L):
+        pl = capi.Plan(L, q, device=local)
+        pl.set_molecules(coefA, coefB)
+        pl.set_experiment(np.ones(6 * len(q)), 1.0, 1.0)
+        pl.set_translations(zv)
+        X = pl.cross_terms(idx)
+        pl.close()
+        return X
+
+    w = build_inputs(capi.expand, capi.opt_params, native_cross, rank, args.nrot, args.nz)
     L, q, zvals, idx = w["L"], w["qvals"], w["zvals"], w["index"]
     n = len(idx)
     plan = capi.Plan(L, q, device=local)
@@ -206,7 +227,7 @@ def run_product(args):
     is64 = idx.dtype == np.int64
     d_idx = torch.from_numpy(idx).to(dev)
     d_out = torch.zeros((3, n), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world, 3, n), dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.empty((world * 3, n), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():

@@ -1,0 +1,330 @@
+"""CPU-side tests (no GPU): the compiled reference against the reference's goldens, the product's host C code
+against the compiled reference, the C-ABI export list, the fit headers compiled for the host, and the
+multi-rank plumbing over gloo.  `oracle/_ref` (the compiled reference) is needed for the comparisons that
+name it; tests skip, not fail, where it is absent (e.g. a checkout without /root/reference)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import refso
+from golden import proto_cross_terms as proto
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+MAP = os.path.join(GOLD, "pdb_formfactor_mapping_clean.prm")
+PRM = os.path.join(GOLD, "atoms.prm")
+
+needs_ref = pytest.mark.skipif(not refso.available(), reason="compiled reference (oracle/_ref) not present")
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from libfmftsaxs_b200 import capi as c
+    c.lib()
+    return c
+
+
+def names(a):
+    return [x.decode() for x in a]
+
+
+# ------------------------------------------------------------------ the oracle against the reference's goldens
+
+@needs_ref
+def test_oracle_reproduces_ref_spf_and_profile(G):
+    """tests/saxs_test.c test_pdb2spf (rel 1e-3) and test_sxs_profile_from_spf (rel 1e-6)"""
+    q, L = G["qvals"], int(G["L"])
+    coef, rm, sa = refso.expand(MAP, G["rec_xyz"], names(G["rec_res"]), names(G["rec_atm"]), G["rec_radius"], q, L,
+                                water_mode=2)
+    assert abs(rm - G["ref_spf_header"][2]) < 5e-5
+    assert np.allclose(sa, G["rec_sa"], rtol=0, atol=1e-15)
+    ref = G["ref_spf"]
+    for c in range(2):
+        mine, r = coef[c], ref[:, :, 2 * c:2 * c + 2]
+        nz = (np.abs(mine) > 0) & (np.abs(r) > 0)
+        assert np.max(np.abs((r - mine)[nz] / r[nz])) < 1e-3
+    assert np.max(np.abs(coef[2] - ref[:, :, 4:6])) / np.abs(ref[:, :, 4:6]).max() < 1e-4
+    i, e = refso.profile_from_spf(coef, L, rm, q, 1.0, 1.0)
+    assert np.max(np.abs(i / G["ref_profile"][:, 1] - 1)) < 1e-6
+    assert np.max(np.abs(e / G["ref_profile"][:, 2] - 1)) < 1e-6
+
+
+@needs_ref
+def test_oracle_reproduces_ref_chi(G):
+    """tests/saxs_test.c score_conformations: 52 rows, abs 1e-3 on chi, c1, c2, exact ft ids"""
+    q, L = G["qvals"], int(G["L"])
+    s, c1, c2 = refso.scores(G["z40_index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, [40.0], L)
+    rc = G["ref_chi"]
+    assert np.array_equal(rc[:, 0].astype(int), G["z40_ft"])
+    assert np.max(np.abs(s - rc[:, 1])) < 1e-3
+    assert np.max(np.abs(c1 - rc[:, 2])) < 1e-3
+    assert np.max(np.abs(c2 - rc[:, 3])) < 1e-3
+    # and the committed full-precision outputs are what the compiled reference gives today
+    assert np.max(np.abs(s / G["z40_scores"] - 1)) < 1e-9
+
+
+@needs_ref
+def test_oracle_reproduces_fitted_profile(G):
+    """tests/saxs_test.c minimize_score; the golden file has 4 decimals, the compiled reference sits 1.03e-6 off"""
+    q, L = G["qvals"], int(G["L"])
+    i, e, o = refso.fitted_profile(G["dimer_coef"], L, G["a_dimer"], G["scal_dimer"], q)
+    assert np.max(np.abs(i / G["ref_fitted_profile"][:, 1] - 1)) < 3e-6
+    assert np.max(np.abs(i / G["fitted_in"] - 1)) < 1e-12
+
+
+# ------------------------------------------------------------------ product host code against the reference
+
+@needs_ref
+def test_host_special_functions_match_reference(capi):
+    rng = np.random.default_rng(0)
+    for x in np.concatenate([rng.uniform(0, 45, 400), [0.0, -1.0, 1e-9, 40.0, 44.99]]):
+        for l in (0, 1, 2, 7, 15, 30, 41):
+            assert capi.sbessel(l, x) == refso.sbessel(l, x)   # bit-identical, incl. the noisy x > 30 range
+    assert np.array_equal(capi.mkarray(0.0, 0.5, 50), refso.mkarray(0.0, 0.5, 50))
+    assert np.array_equal(capi.mkarray(0.0, 0.5, 100), refso.mkarray(0.0, 0.5, 100))
+    M_PI = 3.14159265358
+    for L in (5, 15, 20):
+        for k in (0, 1, L // 2, L):
+            assert np.array_equal(capi.wigner_d(L, k * (M_PI / L)), refso.wigner_d(L, k * (M_PI / L)))
+    for _ in range(500):
+        l, l1 = rng.integers(0, 31, 2)
+        p = rng.integers(abs(l - l1), l + l1 + 1)
+        m = rng.integers(-min(l, l1), min(l, l1) + 1)
+        a, b = capi.wigner_3j(l, p, l1, -m, 0, m), refso.wigner_3j(l, p, l1, -m, 0, m)
+        assert abs(a - b) <= 4e-16 * max(1.0, abs(b))
+
+
+@needs_ref
+def test_host_scoring_tables_match_reference(capi):
+    L = 15
+    ds, dw, tw = capi.tables(L)
+    q = refso.mkarray(0.0, 0.5, 50)
+    dsymb, dwr, bes = proto.reference_tables(L, q, [17.0, 80.0])
+    nb, N = L + 1, 2 * L + 1
+    mine = ds.reshape(nb * nb, nb, N)
+    for l in range(nb):
+        for m in range(-l, l + 1):
+            assert np.max(np.abs(mine[l * (l + 1) + m] - dsymb[l, m + L])) < 1e-14
+    assert np.array_equal(dw.reshape(dwr.shape), dwr)
+    assert np.array_equal(capi.bessel_table([17.0, 80.0], q, L).reshape(bes.shape), bes)
+    step = 2 * 3.14159265358 / N
+    assert np.allclose(tw.reshape(N, 2)[:, 0], np.cos(np.arange(N) * step), rtol=0, atol=1e-15)
+
+
+@needs_ref
+def test_host_pdb_sasa_params_match_reference(capi, G, tmp_path):
+    # atoms as a PDB file written from the fixture, read back by both parsers
+    pdb = tmp_path / "rec.pdb"
+    with open(pdb, "w") as f:
+        for i, (r, a, x) in enumerate(zip(names(G["rec_res"]), names(G["rec_atm"]), G["rec_xyz"] - G["rec_shift"])):
+            f.write("ATOM  %5d %-4s %-4s %4d    %8.3f%8.3f%8.3f  1.00  0.00\n" % (i + 1, a, r.strip(), i // 10 + 1, x[0], x[1], x[2]))
+    mine = capi.load_pdb(str(pdb), PRM, 1)
+    ref = refso.load_pdb(str(pdb), PRM, 1)
+    assert mine["res"] == ref["res"] and mine["atm"] == ref["atm"]
+    assert np.array_equal(mine["xyz"], ref["xyz"]) and np.array_equal(mine["radius"], ref["radius"])
+    assert np.allclose(mine["xyz"], G["rec_xyz"], atol=2e-3)
+    a1, s1 = capi.opt_params(G["exp_q"], G["exp_in"], G["exp_err"], G["qvals"], 1.57)
+    a2, s2 = refso.opt_params(G["exp_q"], G["exp_in"], G["exp_err"], G["qvals"], 1.57)
+    assert np.array_equal(a1, a2) and np.array_equal(s1, s2)
+    assert np.array_equal(a1 * 0 + G["a"], G["a"])
+
+
+@needs_ref
+def test_host_euler_conversion_matches_reference(capi):
+    rng = np.random.default_rng(4)
+    L = 15
+    for _ in range(300):
+        qn = rng.normal(size=4)
+        qn /= np.linalg.norm(qn)
+        w, x, y, z = qn
+        R = np.array([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                      1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w),
+                      1 - 2 * (x * x + y * y)])
+        tv, rl = rng.normal(size=3) * 20, rng.normal(size=3) * 5
+        assert np.array_equal(capi.ft2euler(tv, R, rl), refso.ft2euler(tv, R, rl))
+    # grid snapping incl. the carry quirk (an angle index equal to N spills into the next digit)
+    e = np.array([[40.0, 1.0, 6.2830, 0.001, 2.0, 0.001]])
+    N, nb = 2 * L + 1, L + 1
+    idx = int(capi.euler_to_index(e, [0], L)[0])
+    b_step = 3.14159265358 / L
+    want = ((((0 * nb + round(1.0 / b_step)) * nb + round(2.0 / b_step)) * N + N) * N + N) * N + N  # three digits == N
+    assert idx == want and idx % N == 0  # tools/correlate.c:225-240 adds, it does not wrap
+
+
+def test_workload_indices_follow_correlate_snapping(capi):
+    """the vectorised generator (numpy) and the C snapping agree on the flat index"""
+    from libfmftsaxs_b200 import workload as wl
+    L = 15
+    rng = np.random.default_rng(2)
+    e = np.stack([np.full(200, 40.0), rng.uniform(0.05, 3.09, 200), rng.uniform(0, 6.28, 200), rng.uniform(0, 6.28, 200),
+                  rng.uniform(0.05, 3.09, 200), rng.uniform(0, 6.28, 200)], 1)
+    e = np.round(e, 3)
+    got = capi.euler_to_index(e, np.zeros(200, dtype=np.int32), L)
+    nb, N = L + 1, 2 * L + 1
+    M_PI = wl.M_PI
+    t = np.zeros(200, dtype=np.int64)
+    t = (t + wl._c_round(e[:, 1] / (M_PI / L)).astype(np.int64)) * nb
+    t = (t + wl._c_round(e[:, 4] / (M_PI / L)).astype(np.int64)) * N
+    t = (t + wl._c_round((2 * M_PI - e[:, 3]) / (2 * M_PI / N)).astype(np.int64)) * N
+    t = (t + wl._c_round(e[:, 2] / (2 * M_PI / N)).astype(np.int64)) * N
+    t = t + wl._c_round((2 * M_PI - e[:, 5]) / (2 * M_PI / N)).astype(np.int64)
+    assert np.array_equal(got.astype(np.int64), t)
+
+
+# ------------------------------------------------------------------ C ABI
+
+def test_c_abi_exports_every_declared_symbol(capi):
+    lib = capi.lib()
+    decl = re.compile(r"^\s*(?:const\s+)?(?:unsigned\s+)?(?:struct\s+\w+|\w+)\s*\**\s*(\w+)\s*\(", re.M)
+    missing = []
+    for hdr in ("sxs_cuda.h", "sxs_flat.h", "fftsaxs.h", "pdb2spf.h", "min_saxs.h", "profile.h", "index.h",
+                "saxs_utils.h", "sfbessel.h", "borrowed.h", "form_factor_table.h"):
+        text = open(os.path.join(REPO, "include", "fmftsaxs", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"static inline[^{]*\{.*?\n\}", "", text, flags=re.S)
+        for name in decl.findall(text):
+            if name in ("defined", "if", "while", "return", "sizeof"):
+                continue
+            try:
+                getattr(lib, name)
+            except AttributeError:
+                missing.append(hdr + ":" + name)
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_device(capi):
+    """the compute entry points fail loudly when no CUDA device is present"""
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        capi.cuda_fit_profiles(np.ones((1, 6, 50)), np.ones(300), np.linspace(0, 0.5, 50), 0.4, 1.0)
+    with pytest.raises(RuntimeError):
+        capi.Plan(15, np.linspace(0, 0.5, 50))
+
+
+# ------------------------------------------------------------------ the fit headers, compiled for the host
+
+@pytest.fixture(scope="module")
+def fit_host(tmp_path_factory):
+    out = tmp_path_factory.mktemp("fit") / "libfit_host.so"
+    subprocess.run(["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+                    "-I" + os.path.join(REPO, "libfmftsaxs_b200", "csrc", "cuda"),
+                    os.path.join(HERE, "cpu_harness", "fit_host.c"), "-lm", "-o", str(out)], check=True)
+    lib = ctypes.CDLL(str(out))
+
+    def run(X, a, q, mult, peak):
+        X = np.ascontiguousarray(X)
+        o = np.zeros((len(X), 4))
+        lib.cpu_fit_points(refso.dptr(X), ctypes.c_int(len(X)), refso.dptr(np.ascontiguousarray(a)),
+                           refso.dptr(np.ascontiguousarray(q)), ctypes.c_int(len(q)), ctypes.c_double(mult),
+                           ctypes.c_double(peak), refso.dptr(o))
+        return o
+    return run
+
+
+def test_fit_headers_bitwise_on_fixture(fit_host, G):
+    """K4's optimiser + objective (the very headers the kernel includes), run on the host, against the stored
+    outputs of the reference's L-BFGS-B: bit for bit, including the evaluation counts"""
+    FC = np.load(os.path.join(GOLD, "fit_cases.npz"))
+    X = np.concatenate([FC["X52"], proto.perturbed_family(FC["X52"], 4000, 1)])
+    want = np.concatenate([FC["fit52"], FC["fit_family"]])
+    got = fit_host(X, G["a"], G["qvals"], G["scal"][1], G["scal"][2])
+    assert np.array_equal(got, want)
+
+
+@needs_ref
+def test_fit_headers_bitwise_live(fit_host, G):
+    """fresh experiments with interior optima, bounds, long line searches"""
+    FC = np.load(os.path.join(GOLD, "fit_cases.npz"))
+    X, q = FC["X52"], G["qvals"]
+    rng = np.random.default_rng(9)
+    for fam in range(6):
+        i = rng.integers(0, len(X))
+        c1s, c2s, rm = rng.uniform(0.95, 1.05), rng.uniform(-2.5, 4.5), rng.uniform(1.4, 1.8)
+        mult = (4 * 3.14159265358 / 3) ** 1.5 * rm * rm / (16 * 3.14159265358)
+        Gq = c1s ** 3 * np.exp(-mult * (c1s * c1s - 1) * q * q)
+        x = X[i]
+        I = x[0] - Gq * x[1] + c2s * x[2] + Gq * Gq * x[3] - Gq * c2s * x[4] + c2s * c2s * x[5]
+        eq = np.linspace(0.005, 0.499, int(rng.integers(60, 900)))
+        ei = np.interp(eq, q, I) * 1e-6
+        ee = ei * 0.05 + 1e-12
+        ei = ei + rng.normal(0, 1, len(eq)) * ee
+        a, scal = refso.opt_params(eq, ei, ee, q, rm)
+        fam_x = proto.perturbed_family(X, 300, 100 + fam)
+        want = refso.fit(fam_x, a, scal, q, True)
+        got = fit_host(fam_x, a, q, scal[1], scal[2])
+        assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ multi-rank plumbing (gloo, world size 2)
+
+def test_z_sharding_covers_every_pose_once():
+    from libfmftsaxs_b200 import dist as sd
+    from libfmftsaxs_b200 import workload as wl
+    idx = wl.make_pose_indices(15, np.arange(17.0, 25.0), 500, 3)
+    for world in (1, 2, 3, 8, 16):
+        ranges = sd.shard_z_ranges(idx, 15, 8, world)
+        own = sd.owners_of(idx, 15, ranges)
+        assert (own >= 0).all()
+        assert ranges[0][0] == 0 and ranges[-1][1] == 8
+        counts = np.bincount(own, minlength=world)
+        if world <= 8:
+            assert counts.max() - counts.min() <= 2 * 500  # at most one z step of imbalance either way
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {repo!r}); sys.path.insert(0, {tests!r})
+import numpy as np, torch, torch.distributed as dist
+import refso
+from libfmftsaxs_b200 import dist as sd
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+G = np.load({gold!r})
+q, L = G["qvals"], int(G["L"])
+idx, zv = G["z6_index"], G["z6_zvals"]
+# (1) z-sharded scoring of ONE list (the reference's MPI scheme): each rank scores its z range, tables merged
+ranges = sd.shard_z_ranges(idx, L, len(zv), world)
+lo, hi = ranges[rank]
+keep = (sd.z_digit(idx, L) >= lo) & (sd.z_digit(idx, L) < hi) & (np.arange(len(idx)) % 29 == 0)  # thin: CPU oracle is slow
+s = np.zeros(len(idx)); c1 = np.zeros(len(idx)); c2 = np.zeros(len(idx))
+if keep.any():
+    r = refso.scores(idx[keep], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
+    s[keep], c1[keep], c2[keep] = r
+local = torch.from_numpy(np.stack([s, c1, c2]))
+allt = sd.all_gather_tables(local).numpy()
+thin = np.arange(len(idx)) % 29 == 0
+own = sd.owners_of(idx, L, ranges)
+merged = sd.merge_tables([tuple(allt[r]) for r in range(world)], own)
+ok = np.max(np.abs(merged[0][thin] / G["z6_scores"][thin] - 1)) < 1e-9 and np.max(np.abs(merged[1][thin] / G["z6_c1"][thin] - 1)) < 1e-6
+# (2) the gathered tensor is identical on every rank
+chk = torch.tensor([float(allt.sum())], dtype=torch.float64)
+lst = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+dist.all_gather(lst, chk)
+same = all(abs(float(x) - float(chk)) == 0.0 for x in lst)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if (ok and same) else 3)
+'''
+
+
+@needs_ref
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(repo=REPO, tests=HERE, gold=os.path.join(GOLD, "golden_4g9s.npz")))
+    port = 29500 + (os.getpid() % 2000)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
