@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libfmftsaxs.so")
+LIB_PATH = os.environ.get("SXS_LIB_PATH") or os.path.join(PKG, "libfmftsaxs.so")  # override: tuning builds only
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -1230,8 +1230,9 @@ LB_FN void lb_dcsrch(struct lb_state *s, double f, double g, double *stp, double
  * GPU warp run 32 independent fits in lock-step: the optimiser logic diverges, the expensive
  * objective is evaluated convergently by all lanes.
  */
-enum lb_phase { LB_PH_INIT = 0, LB_PH_FIRST_EVAL, LB_PH_LINESEARCH, LB_PH_DONE };
-enum lb_status { LB_DONE = 0, LB_NEED_EVAL = 1 };
+enum lb_phase { LB_PH_INIT = 0, LB_PH_FIRST_EVAL, LB_PH_LINESEARCH, LB_PH_DONE,
+                LB_PH_B_FIRST, LB_PH_B_ACCEPTED, LB_PH_B_NEW_ITER };
+enum lb_status { LB_DONE = 0, LB_NEED_EVAL = 1, LB_NEED_B = 2 };
 
 LB_FN void lb_begin(struct lb_state *s, double x1, double x2, double l1, double u1, double l2, double u2, double factr)
 {
@@ -1273,34 +1274,125 @@ LB_FN void lb_begin(struct lb_state *s, double x1, double x2, double l1, double 
 	s->phase = LB_PH_INIT;
 }
 
-LB_FN int lb_step(struct lb_state *s, const double pgtol)
+/* One turn of the line search with f, g at the current x (labels 666/556 of mainlb plus the
+ * bookkeeping that follows lnsrlb's return, lbfgsb.c:871-915).  Outcomes:
+ *   LB_PH_LINESEARCH   a new trial x was written, the objective is wanted there
+ *   LB_PH_B_ACCEPTED   the search ended normally: iterate accepted
+ *   LB_PH_B_NEW_ITER   the search failed with memory in use: memory reset, start a new iteration
+ *   LB_PH_DONE         abnormal termination with empty memory: previous iterate restored */
+LB_FN int lb_linesearch_turn(struct lb_state *s)
 {
-	int info_ls;
+	int info_ls = 0;
+	int search_over = 0;
+	{
+		double acc = 0.0;
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			acc += s->g[i] * s->d[i];
+		}
+		s->gd = acc;
+	}
+	if (s->ifun == 0) {
+		s->gdold = s->gd;
+		if (s->gd >= 0.0) {
+			info_ls = -4; /* ascent direction in projection */
+		}
+	}
+	if (info_ls == 0) {
+		lb_dcsrch(s, s->f, s->gd, &s->stp, s->stpmx);
+		if (s->ls_task == LS_FG) {
+			++s->ifun;
+			++s->nfgv;
+			s->iback = s->ifun - 1;
+			if (s->stp == 1.0) {
+				LB_NOUNROLL
+				for (int i = 1; i <= LB_N; i++) {
+					s->x[i] = s->z[i];
+				}
+			} else {
+				LB_NOUNROLL
+				for (int i = 1; i <= LB_N; i++) {
+					s->x[i] = s->stp * s->d[i] + s->t[i];
+				}
+			}
+		} else {
+			search_over = 1;
+		}
+	}
+	if (info_ls != 0 || s->iback >= 20) {
+		/* restore the previous iterate */
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			s->x[i] = s->t[i];
+			s->g[i] = s->r[i];
+		}
+		s->f = s->fold;
+		if (s->col == 0) {
+			/* abnormal termination in the line search */
+			if (info_ls == 0) {
+				--s->nfgv;
+				--s->ifun;
+				--s->iback;
+			}
+			++s->iter;
+			return LB_PH_DONE;
+		}
+		if (info_ls == 0) {
+			--s->nfgv;
+		}
+		lb_reset_memory(s);
+		return LB_PH_B_NEW_ITER;
+	}
+	return search_over ? LB_PH_B_ACCEPTED : LB_PH_LINESEARCH;
+}
 
+/* Part A — what every fit does right after an objective evaluation: cheap, and the same code for
+ * (nearly) all lanes.  Returns LB_NEED_EVAL, LB_NEED_B (s->phase says where part B enters) or LB_DONE. */
+LB_FN int lb_step_a(struct lb_state *s)
+{
 	if (s->phase == LB_PH_LINESEARCH) {
-		goto after_linesearch_eval;
+		s->phase = lb_linesearch_turn(s);
+		if (s->phase == LB_PH_LINESEARCH) {
+			return LB_NEED_EVAL;
+		}
+		return s->phase == LB_PH_DONE ? LB_DONE : LB_NEED_B;
 	}
 	if (s->phase == LB_PH_FIRST_EVAL) {
-		goto after_first_eval;
+		s->phase = LB_PH_B_FIRST;
+		return LB_NEED_B;
 	}
-	if (s->phase == LB_PH_DONE) {
-		return LB_DONE;
-	}
-
-	/* active(): project the start into the box, all variables boxed (subalgorithms.c:7-118) */
-	LB_NOUNROLL
-	for (int i = 1; i <= LB_N; i++) {
-		if (s->x[i] <= s->l[i]) {
-			s->x[i] = s->l[i];
-		} else if (s->x[i] >= s->u[i]) {
-			s->x[i] = s->u[i];
+	if (s->phase == LB_PH_INIT) {
+		/* active(): project the start into the box, all variables boxed (subalgorithms.c:7-118) */
+		LB_NOUNROLL
+		for (int i = 1; i <= LB_N; i++) {
+			if (s->x[i] <= s->l[i]) {
+				s->x[i] = s->l[i];
+			} else if (s->x[i] >= s->u[i]) {
+				s->x[i] = s->u[i];
+			}
+			s->iwhere[i] = (s->u[i] - s->l[i] <= 0.0) ? 3 : 0;
 		}
-		s->iwhere[i] = (s->u[i] - s->l[i] <= 0.0) ? 3 : 0;
+		s->phase = LB_PH_FIRST_EVAL;
+		return LB_NEED_EVAL;
 	}
-	s->phase = LB_PH_FIRST_EVAL;
-	return LB_NEED_EVAL;
+	return s->phase == LB_PH_DONE ? LB_DONE : LB_NEED_B;
+}
 
-after_first_eval:
+/* Part B — the iteration boundary: convergence tests, BFGS update, generalised Cauchy point,
+ * subspace minimisation, line-search set-up and its first turn.  Long and branchy; the GPU kernel
+ * runs it on warps packed with exactly the fits that need it.  Returns LB_NEED_EVAL or LB_DONE. */
+LB_FN int lb_step_b(struct lb_state *s, const double pgtol)
+{
+	if (s->phase == LB_PH_B_NEW_ITER) {
+		goto new_iteration;
+	}
+	if (s->phase == LB_PH_B_ACCEPTED) {
+		goto accepted;
+	}
+	if (s->phase != LB_PH_B_FIRST) {
+		return s->phase == LB_PH_DONE ? LB_DONE : LB_NEED_EVAL;
+	}
+
 	s->nfgv = 1;
 	s->sbgnrm = lb_projgr(s);
 	if (s->sbgnrm <= pgtol) {
@@ -1383,75 +1475,20 @@ new_iteration: /* label 222 of mainlb */
 	s->iback = 0;
 	s->ls_task = LS_START;
 
-after_linesearch_eval: /* label 666/556: one turn of the search with f, g at the current x */
-	info_ls = 0;
-	{
-		double acc = 0.0;
-		LB_NOUNROLL
-		for (int i = 1; i <= LB_N; i++) {
-			acc += s->g[i] * s->d[i];
-		}
-		s->gd = acc;
+	/* first turn of the search: uses f, g at the current iterate, no new evaluation needed */
+	s->phase = lb_linesearch_turn(s);
+	if (s->phase == LB_PH_LINESEARCH) {
+		return LB_NEED_EVAL;
 	}
-	{
-		int search_over = 0;
-		if (s->ifun == 0) {
-			s->gdold = s->gd;
-			if (s->gd >= 0.0) {
-				info_ls = -4; /* ascent direction in projection */
-			}
-		}
-		if (info_ls == 0) {
-			lb_dcsrch(s, s->f, s->gd, &s->stp, s->stpmx);
-			if (s->ls_task == LS_FG) {
-				++s->ifun;
-				++s->nfgv;
-				s->iback = s->ifun - 1;
-				if (s->stp == 1.0) {
-					LB_NOUNROLL
-					for (int i = 1; i <= LB_N; i++) {
-						s->x[i] = s->z[i];
-					}
-				} else {
-					LB_NOUNROLL
-					for (int i = 1; i <= LB_N; i++) {
-						s->x[i] = s->stp * s->d[i] + s->t[i];
-					}
-				}
-			} else {
-				search_over = 1;
-			}
-		}
-		if (info_ls != 0 || s->iback >= 20) {
-			/* restore the previous iterate */
-			LB_NOUNROLL
-			for (int i = 1; i <= LB_N; i++) {
-				s->x[i] = s->t[i];
-				s->g[i] = s->r[i];
-			}
-			s->f = s->fold;
-			if (s->col == 0) {
-				/* abnormal termination in the line search */
-				if (info_ls == 0) {
-					--s->nfgv;
-					--s->ifun;
-					--s->iback;
-				}
-				++s->iter;
-				goto finished;
-			}
-			if (info_ls == 0) {
-				--s->nfgv;
-			}
-			lb_reset_memory(s);
-			goto new_iteration;
-		}
-		if (!search_over) {
-			s->phase = LB_PH_LINESEARCH;
-			return LB_NEED_EVAL;
-		}
+	if (s->phase == LB_PH_B_NEW_ITER) {
+		goto new_iteration;
 	}
-	/* ---- new iterate accepted (label 777) ---- */
+	if (s->phase == LB_PH_DONE) {
+		return LB_DONE;
+	}
+	/* LB_PH_B_ACCEPTED cannot follow a START turn (the search always asks for one evaluation) */
+
+accepted: /* label 777 */
 	++s->iter;
 	s->sbgnrm = lb_projgr(s);
 	if (s->sbgnrm <= pgtol) {
@@ -1502,6 +1539,16 @@ after_linesearch_eval: /* label 666/556: one turn of the search with f, g at the
 finished:
 	s->phase = LB_PH_DONE;
 	return LB_DONE;
+}
+
+/* Serial composition of the two parts (host harness, single fits). */
+LB_FN int lb_step(struct lb_state *s, const double pgtol)
+{
+	int r = lb_step_a(s);
+	if (r == LB_NEED_B) {
+		r = lb_step_b(s, pgtol);
+	}
+	return r;
 }
 
 #endif /* SXS_LBFGSB_N2M3_H */

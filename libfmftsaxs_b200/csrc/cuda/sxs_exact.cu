@@ -20,7 +20,12 @@
 #include "fit_point.h"
 
 #define SXS_FIT_MAXQ 512
+#ifndef SXS_FIT_THREADS
 #define SXS_FIT_THREADS 128
+#endif
+#ifndef SXS_FIT_MINBLOCKS
+#define SXS_FIT_MINBLOCKS 6
+#endif
 
 /* K4.  X is point-major: the 6*qnum cross terms of point p are the contiguous row X[p*6*qnum + q*6 + k]
  * (2.4 KB at Q = 50), read with 16-byte loads.
@@ -30,8 +35,9 @@
  * branchy and diverges between lanes, the objective (2 passes over q with an exp each, ~95 % of the
  * arithmetic) is executed convergently.  A lane whose fit has terminated takes the next point from a
  * global ticket counter at the top of the next round, so lanes do not idle while a neighbour finishes a
- * long line search (evaluations per fit range from 2 to ~50). */
-__global__ void __launch_bounds__(SXS_FIT_THREADS)
+ * long line search (evaluations per fit range from 2 to ~60).
+ * Variants measured and rejected are logged in profiles/r1_k4_notes.md. */
+__global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {

@@ -1,0 +1,91 @@
+"""CLI contract: our `correlate` / `single_saxs` binaries against the reference's own tools (compiled unmodified
+into oracle/_ref) on the same files — argument list, Euler side file, output rows and their order."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import refso
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+GOLD = os.path.join(HERE, "golden")
+MAP = os.path.join(GOLD, "pdb_formfactor_mapping_clean.prm")
+PRM = os.path.join(GOLD, "atoms.prm")
+BIN = os.path.join(REPO, "libfmftsaxs_b200", "bin")
+REF = os.path.join(REPO, "oracle", "_ref")
+
+pytestmark = pytest.mark.gpu
+
+
+def write_pdb(path, res, atm, xyz):
+    with open(path, "w") as f:
+        f.write("REMARK fixture\n")
+        for i, (r, a, x) in enumerate(zip(res, atm, xyz)):
+            f.write("ATOM  %5d %-4s %-4s %4d    %8.3f%8.3f%8.3f  1.00  0.00\n" % (i + 1, a.decode(), r.decode().strip(), i // 10 + 1, x[0], x[1], x[2]))
+        f.write("END\n")
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+    d = tmp_path_factory.mktemp("cli")
+    write_pdb(d / "rec.pdb", G["rec_res"], G["rec_atm"], G["rec_xyz"] - G["rec_shift"])
+    write_pdb(d / "lig.pdb", G["lig_res"], G["lig_atm"], G["lig_xyz"] - G["lig_shift"])
+    with open(d / "exp.dat", "w") as f:
+        for q, i, e in zip(G["exp_q"], G["exp_in"], G["exp_err"]):
+            f.write(" %.6e  %.6e  %.6e\n" % (q, i, e))
+    rng = np.random.default_rng(21)
+    nrot, nrow = 40, 48
+    with open(d / "rot.prm", "w") as f:
+        for k in range(nrot):
+            qn = rng.normal(size=4)
+            qn /= np.linalg.norm(qn)
+            w, x, y, z = qn
+            R = [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                 1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]
+            f.write("%d " % k + " ".join("%.9f" % v for v in R) + "\n")
+    # ligand centre relative to receptor centre in the input frames = -(com - coe) with the stored negated shifts
+    ref_lig = -(G["lig_shift"] - G["rec_shift"])
+    with open(d / "ft.000", "w") as f:
+        for k in range(nrow):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            dist = rng.choice([38.0, 39.0, 95.0]) + rng.uniform(-0.3, 0.3)   # 95 A is off the 1..80 table: row dropped
+            t = dist * u - ref_lig
+            f.write("%d %.3f %.3f %.3f 0.0 0.0 0.0 0.0 0.0 0.0\n" % (rng.integers(0, nrot), t[0], t[1], t[2]))
+    return d
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_correlate")), reason="compiled reference tools not present")
+def test_correlate_cli_matches_reference_tool(files):
+    d = files
+    common = [MAP, PRM, str(d / "ft.000"), str(d / "rot.prm"), str(d / "rec.pdb"), str(d / "lig.pdb"), str(d / "exp.dat"), "15"]
+    r1 = subprocess.run([os.path.join(BIN, "correlate")] + common + [str(d / "eul_ours"), str(d / "out_ours")],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stdout[-2000:]
+    assert "Time passed:" in r1.stdout and "Correlation finished" in r1.stdout
+    r2 = subprocess.run([os.path.join(REF, "ref_correlate")] + common + [str(d / "eul_ref"), str(d / "out_ref")],
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r2.returncode == 0, r2.stdout[-2000:]
+    assert open(d / "eul_ours").read() == open(d / "eul_ref").read()
+    ours = [l.split("\t") for l in open(d / "out_ours").read().splitlines()]
+    ref = [l.split("\t") for l in open(d / "out_ref").read().splitlines()]
+    assert len(ours) == len(ref) and 0 < len(ours) < 48          # the 95 A rows are dropped by both
+    for a, b in zip(ours, ref):
+        assert a[0].strip() == b[0].strip() and a[1] == b[1]       # serial and ft id, same order
+        for x, y in zip(a[2:], b[2:]):
+            assert abs(float(x) - float(y)) <= 1.001e-3            # "%.3lf" columns
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_single_saxs")), reason="compiled reference tools not present")
+def test_single_saxs_cli_matches_reference_tool(files):
+    d = files
+    for L in ("10", "15", "20"):                                   # examples/run_single_saxs.sh sweep of BASELINE config 2
+        common = [MAP, PRM, str(d / "rec.pdb"), str(d / "lig.pdb"), "1.0", "0.0", L]
+        subprocess.run([os.path.join(BIN, "single_saxs")] + common + [str(d / "p_ours")], check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([os.path.join(REF, "ref_single_saxs")] + common + [str(d / "p_ref")], check=True, stdout=subprocess.DEVNULL)
+        a, b = np.loadtxt(d / "p_ours"), np.loadtxt(d / "p_ref")
+        assert a.shape == b.shape == (50, 3)
+        assert np.max(np.abs(a[:, 1] / b[:, 1] - 1)) < 1e-6
