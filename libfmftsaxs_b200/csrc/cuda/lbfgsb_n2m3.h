@@ -89,71 +89,75 @@ SXS_HD void lb_reset_memory(struct lb_state *s)
 	s->updatd = 0;
 }
 
-/* Cholesky factor (upper) of the n x n block of `a` whose (1,1) sits at a[r0+1][c0+1];
- * LINPACK dpofa, lbfgsb/src/linpack.c:11-109.  a is addressed a[row][col]. */
-#define LB_DPOFA(NAME, DIM)                                                                           \
-	LB_FN int NAME(double (*a)[DIM + 1], int off, int n)                                              \
-	{                                                                                                 \
-		LB_NOUNROLL for (int j = 1; j <= n; j++) {                                                                \
-			double sacc = 0.0;                                                                        \
-			LB_NOUNROLL for (int k = 1; k <= j - 1; k++) {                                                        \
-				double dot = 0.0;                                                                     \
-				LB_NOUNROLL for (int i = 1; i <= k - 1; i++) {                                                    \
-					dot += a[off + i][off + k] * a[off + i][off + j];                                 \
-				}                                                                                     \
-				double tt = a[off + k][off + j] - dot;                                                \
-				tt /= a[off + k][off + k];                                                            \
-				a[off + k][off + j] = tt;                                                             \
-				sacc += tt * tt;                                                                      \
-			}                                                                                         \
-			sacc = a[off + j][off + j] - sacc;                                                        \
-			if (sacc <= 0.0) {                                                                        \
-				return j;                                                                             \
-			}                                                                                         \
-			a[off + j][off + j] = sqrt(sacc);                                                         \
-		}                                                                                             \
-		return 0;                                                                                     \
+/* Cholesky factor (upper) of the n x n block of `a` whose (1,1) sits at row/column off+1;
+ * LINPACK dpofa, lbfgsb/src/linpack.c:11-109.  a is a row-major [ld][ld] array addressed a[row*ld + col]
+ * (1-based rows and columns, like the state struct).  One instance serves the m x m and 2m x 2m
+ * matrices: code size matters more than the constant stride here (see the note above LB_FN). */
+LB_FN int lb_dpofa(double *a, int ld, int off, int n)
+{
+	LB_NOUNROLL
+	for (int j = 1; j <= n; j++) {
+		double sacc = 0.0;
+		LB_NOUNROLL
+		for (int k = 1; k <= j - 1; k++) {
+			double dot = 0.0;
+			LB_NOUNROLL
+			for (int i = 1; i <= k - 1; i++) {
+				dot += a[(off + i) * ld + off + k] * a[(off + i) * ld + off + j];
+			}
+			double tt = a[(off + k) * ld + off + j] - dot;
+			tt /= a[(off + k) * ld + off + k];
+			a[(off + k) * ld + off + j] = tt;
+			sacc += tt * tt;
+		}
+		sacc = a[(off + j) * ld + off + j] - sacc;
+		if (sacc <= 0.0) {
+			return j;
+		}
+		a[(off + j) * ld + off + j] = sqrt(sacc);
 	}
-LB_DPOFA(lb_dpofa_m, LB_M)
-LB_DPOFA(lb_dpofa_2m, LB_M2)
+	return 0;
+}
 
-/* Triangular solves with an upper-triangular factor stored in t[row][col] (LINPACK dtrsl,
+/* Triangular solves with an upper-triangular factor stored in t[row*ld + col] (LINPACK dtrsl,
  * lbfgsb/src/linpack.c:111-297): job 11 solves trans(T) x = b, job 01 solves T x = b. */
-#define LB_DTRSL(NAME, DIM)                                                                           \
-	LB_FN int NAME(double (*t)[DIM + 1], int n, double *b, int job)                                   \
-	{                                                                                                 \
-		LB_NOUNROLL for (int i = 1; i <= n; i++) {                                                                \
-			if (t[i][i] == 0.0) {                                                                     \
-				return i;                                                                             \
-			}                                                                                         \
-		}                                                                                             \
-		if (job == 11) {                                                                              \
-			b[1] /= t[1][1];                                                                          \
-			LB_NOUNROLL for (int j = 2; j <= n; j++) {                                                            \
-				double dot = 0.0;                                                                     \
-				LB_NOUNROLL for (int i = 1; i <= j - 1; i++) {                                                    \
-					dot += t[i][j] * b[i];                                                            \
-				}                                                                                     \
-				b[j] -= dot;                                                                          \
-				b[j] /= t[j][j];                                                                      \
-			}                                                                                         \
-		} else { /* job == 01 */                                                                      \
-			b[n] /= t[n][n];                                                                          \
-			LB_NOUNROLL for (int jj = 2; jj <= n; jj++) {                                                         \
-				int j = n - jj + 1;                                                                   \
-				double temp = -b[j + 1];                                                              \
-				if (temp != 0.0) {                                                                    \
-					LB_NOUNROLL for (int i = 1; i <= j; i++) {                                                    \
-						b[i] += temp * t[i][j + 1];                                                   \
-					}                                                                                 \
-				}                                                                                     \
-				b[j] /= t[j][j];                                                                      \
-			}                                                                                         \
-		}                                                                                             \
-		return 0;                                                                                     \
+LB_FN int lb_dtrsl(const double *t, int ld, int n, double *b, int job)
+{
+	LB_NOUNROLL
+	for (int i = 1; i <= n; i++) {
+		if (t[i * ld + i] == 0.0) {
+			return i;
+		}
 	}
-LB_DTRSL(lb_dtrsl_m, LB_M)
-LB_DTRSL(lb_dtrsl_2m, LB_M2)
+	if (job == 11) {
+		b[1] /= t[1 * ld + 1];
+		LB_NOUNROLL
+		for (int j = 2; j <= n; j++) {
+			double dot = 0.0;
+			LB_NOUNROLL
+			for (int i = 1; i <= j - 1; i++) {
+				dot += t[i * ld + j] * b[i];
+			}
+			b[j] -= dot;
+			b[j] /= t[j * ld + j];
+		}
+	} else { /* job == 01 */
+		b[n] /= t[n * ld + n];
+		LB_NOUNROLL
+		for (int jj = 2; jj <= n; jj++) {
+			int j = n - jj + 1;
+			double temp = -b[j + 1];
+			if (temp != 0.0) {
+				LB_NOUNROLL
+				for (int i = 1; i <= j; i++) {
+					b[i] += temp * t[i * ld + j + 1];
+				}
+			}
+			b[j] /= t[j * ld + j];
+		}
+	}
+	return 0;
+}
 
 /* Product of the 2m x 2m middle matrix of the compact L-BFGS formula with a 2*col vector
  * (subalgorithms.c bmv, :120-259). */
@@ -176,7 +180,7 @@ LB_FN int lb_bmv(const struct lb_state *s, const double *v, double *p)
 		}
 		p[i2] = v[i2] + sum;
 	}
-	int info = lb_dtrsl_m((double (*)[LB_M + 1])s->wt, col, &p[col], 11);
+	int info = lb_dtrsl(&s->wt[0][0], LB_M + 1, col, &p[col], 11);
 	if (info != 0) {
 		return info;
 	}
@@ -186,7 +190,7 @@ LB_FN int lb_bmv(const struct lb_state *s, const double *v, double *p)
 	}
 	/* solve [ -D^(1/2)  D^(-1/2)*L' ] [ p1 ] = [ p1 ]
 	 *       [ 0         J'          ] [ p2 ]   [ p2 ]  */
-	info = lb_dtrsl_m((double (*)[LB_M + 1])s->wt, col, &p[col], 1);
+	info = lb_dtrsl(&s->wt[0][0], LB_M + 1, col, &p[col], 1);
 	if (info != 0) {
 		return info;
 	}
@@ -728,7 +732,7 @@ LB_FN int lb_formk(struct lb_state *s)
 		wn[iy][iy] += s->sy[iy][iy];
 	}
 	/* first Cholesky: (1,1) block of WN */
-	if (lb_dpofa_2m(wn, 0, col) != 0) {
+	if (lb_dpofa(&wn[0][0], LB_M2 + 1, 0, col) != 0) {
 		return -1;
 	}
 	/* then form L^-1(-L_a'+R_z') in the (1,2) block */
@@ -741,7 +745,7 @@ LB_FN int lb_formk(struct lb_state *s)
 		for (int i = 1; i <= col; i++) {
 			b[i] = wn[i][js];
 		}
-		(void)lb_dtrsl_2m(wn, col, b, 11);
+		(void)lb_dtrsl(&wn[0][0], LB_M2 + 1, col, b, 11);
 		LB_NOUNROLL
 		for (int i = 1; i <= col; i++) {
 			wn[i][js] = b[i];
@@ -761,7 +765,7 @@ LB_FN int lb_formk(struct lb_state *s)
 		}
 	}
 	/* Cholesky factorisation of the (2,2) block */
-	if (lb_dpofa_2m(wn, col, col) != 0) {
+	if (lb_dpofa(&wn[0][0], LB_M2 + 1, col, col) != 0) {
 		return -2;
 	}
 	return 0;
@@ -824,7 +828,7 @@ LB_FN int lb_subsm(struct lb_state *s)
 	/* wv := K^-1 wv, K = LEL' stored as the upper-triangular factor in wn; the 2col x 2col system
 	 * lives in the leading rows/columns of wn (its two blocks were packed contiguously by formk) */
 	const int col2 = 2 * col;
-	int info = lb_dtrsl_2m(s->wn, col2, wv, 11);
+	int info = lb_dtrsl(&s->wn[0][0], LB_M2 + 1, col2, wv, 11);
 	if (info != 0) {
 		return info;
 	}
@@ -832,7 +836,7 @@ LB_FN int lb_subsm(struct lb_state *s)
 	for (int i = 1; i <= col; i++) {
 		wv[i] = -wv[i];
 	}
-	info = lb_dtrsl_2m(s->wn, col2, wv, 1);
+	info = lb_dtrsl(&s->wn[0][0], LB_M2 + 1, col2, wv, 1);
 	if (info != 0) {
 		return info;
 	}
@@ -1009,7 +1013,7 @@ LB_FN int lb_formt(struct lb_state *s)
 			s->wt[i][j] = ddum + s->theta * s->ss[i][j];
 		}
 	}
-	if (lb_dpofa_m(s->wt, 0, col) != 0) {
+	if (lb_dpofa(&s->wt[0][0], LB_M + 1, 0, col) != 0) {
 		return -3;
 	}
 	return 0;

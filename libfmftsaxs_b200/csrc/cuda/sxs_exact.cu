@@ -40,7 +40,6 @@
  * global ticket counter at the top of the next round, so lanes do not idle while a neighbour finishes a
  * long line search (evaluations per fit range from 2 to ~60).
  * Variants measured and rejected are logged in profiles/r1_k4_notes.md. */
-template <int ROWCAP>
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
@@ -60,10 +59,6 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	struct sxs_fit_ctx ctx;
 	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
 	ctx.x = X; ctx.scale = 1.0;
-	/* Private copy of the fit's 6*qnum cross terms.  Thread-local memory is lane-interleaved, so the ~40
-	 * passes an average fit makes over its row become coalesced warp loads (4 lines per 16-byte load
-	 * instead of 32 when every lane streams its own global row). */
-	double2 xl[ROWCAP > 0 ? ROWCAP / 2 : 1];
 	long long p = -1;
 	bool have = false, drained = false;
 
@@ -72,13 +67,6 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 			p = (long long)atomicAdd(ticket, 1ull);
 			if (p < npts) {
 				ctx.x = X + (size_t)p * 6 * qnum;
-				if (ROWCAP > 0) {
-					const double2 *src = reinterpret_cast<const double2 *>(ctx.x);
-					for (int i = 0; i < 3 * qnum; i++) {
-						xl[i] = src[i];
-					}
-					ctx.x = reinterpret_cast<const double *>(xl);
-				}
 				ctx.scale = 1.0;
 				if (rescale) {
 					ctx.scale = sxs_fit_rescale(&ctx, peak);
@@ -135,10 +123,7 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	const size_t shm = sizeof(double) * 7 * qnum;
-	const int rowcap = getenv("SXS_FIT_GLOBAL_ROWS") ? 0 : (6 * qnum <= 384 ? 384 : (6 * qnum <= 768 ? 768 : 0));
-	void (*kern)(const double *, long long, const double *, const double *, int, double, double, int, double *,
-	             unsigned long long *) = rowcap == 384 ? k_fit<384> : (rowcap == 768 ? k_fit<768> : k_fit<0>);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SXS_FIT_THREADS, shm);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
 	if (per_sm < 1) per_sm = 1;
 	if (getenv("SXS_FIT_BLOCKS_PER_SM")) { /* tuning only */
 		const int v = atoi(getenv("SXS_FIT_BLOCKS_PER_SM"));
@@ -148,7 +133,7 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	const long long need = (npts + SXS_FIT_THREADS - 1) / SXS_FIT_THREADS;
 	if (blocks > need) blocks = need;
 	SXS_CK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), stream));
-	kern<<<(unsigned)blocks, SXS_FIT_THREADS, shm, stream>>>(d_x, npts, d_a, d_qvals, qnum, mult, peak, rescale, d_res, d_ticket);
+	k_fit<<<(unsigned)blocks, SXS_FIT_THREADS, shm, stream>>>(d_x, npts, d_a, d_qvals, qnum, mult, peak, rescale, d_res, d_ticket);
 	SXS_CK_LAUNCH();
 	return 0;
 }
