@@ -96,6 +96,7 @@ struct sxs_cuda_plan {
 	void *d_index_in; size_t cap_index_in;
 	double *d_out3; size_t cap_out3;
 	long long *h_zoff;
+	void *h_pinned; size_t cap_pinned;
 	/* budgets */
 	size_t budget_St, budget_X;
 	long long stats[5];
@@ -237,6 +238,9 @@ extern "C" void sxs_cuda_plan_destroy(sxs_cuda_plan *p)
 	}
 	if (p->h_zoff != NULL) {
 		cudaFreeHost(p->h_zoff);
+	}
+	if (p->h_pinned != NULL) {
+		cudaFreeHost(p->h_pinned);
 	}
 	free(p);
 }
@@ -677,12 +681,14 @@ extern "C" int sxs_cuda_plan_set_translations(sxs_cuda_plan *p, const double *be
 		sxs_cuda_set_error("znum %d out of range", znum);
 		return -1;
 	}
-	if (p->d_bessel != NULL) {
+	const size_t n = (size_t)znum * p->qnum * p->N;
+	if (p->d_bessel != NULL && znum != p->znum) {
 		cudaFree(p->d_bessel);
 		p->d_bessel = NULL;
 	}
-	const size_t n = (size_t)znum * p->qnum * p->N;
-	SXS_CK(cudaMalloc(&p->d_bessel, sizeof(double) * n));
+	if (p->d_bessel == NULL) {
+		SXS_CK(cudaMalloc(&p->d_bessel, sizeof(double) * n));
+	}
 	SXS_CK(cudaMemcpy(p->d_bessel, bessel, sizeof(double) * n, cudaMemcpyHostToDevice));
 	p->znum = znum;
 	return 0;
@@ -930,31 +936,43 @@ static int score_host(sxs_cuda_plan *p, const IndexT *index, long long nout, int
 	}
 	if (ensure(&p->d_out3, &p->cap_out3, (size_t)nout * 3)) return -1;
 	SXS_CK(cudaMemcpy(p->d_index_in, index, sizeof(IndexT) * (size_t)nout, cudaMemcpyHostToDevice));
+	/* results are scattered to list order on the device: d_out3 = [scores | c1 | c2], nout each */
+	double *d_s = p->d_out3, *d_c1 = p->d_out3 + nout, *d_c2 = p->d_out3 + 2 * nout;
 	long long nvalid = 0;
-	if (score_core<IndexT>(p, (const IndexT *)p->d_index_in, nout, z_lo, z_hi, NULL, NULL, NULL, p->d_out3, NULL, 0, &nvalid) != 0) {
+	if (score_core<IndexT>(p, (const IndexT *)p->d_index_in, nout, z_lo, z_hi, d_s, d_c1, d_c2, NULL, NULL, 0, &nvalid) != 0) {
 		return -1;
 	}
 	SXS_CK(cudaDeviceSynchronize());
 	if (nvalid == 0) {
 		return 0;
 	}
-	double *h3 = (double *)malloc(sizeof(double) * 3 * (size_t)nvalid);
-	unsigned int *hrows = (unsigned int *)malloc(sizeof(unsigned int) * (size_t)nvalid);
-	if (h3 == NULL || hrows == NULL) {
-		sxs_cuda_set_error("host allocation failed");
-		free(h3); free(hrows);
-		return -1;
+	if (nvalid == nout) {
+		/* every row was scored: three straight copies into the caller's arrays */
+		SXS_CK(cudaMemcpy(scores, d_s, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost));
+		SXS_CK(cudaMemcpy(c1, d_c1, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost));
+		SXS_CK(cudaMemcpy(c2, d_c2, sizeof(double) * (size_t)nout, cudaMemcpyDeviceToHost));
+		return 0;
 	}
-	SXS_CK(cudaMemcpy(h3, p->d_out3, sizeof(double) * 3 * (size_t)nvalid, cudaMemcpyDeviceToHost));
+	/* Partial coverage (a z shard of a multi-GPU call, or rows off the z table): unscored rows must keep the
+	 * caller's values and other shards write the same arrays concurrently, so only this call's rows are touched. */
+	const size_t need = sizeof(double) * 3 * (size_t)nout + sizeof(unsigned int) * (size_t)nvalid;
+	if (need > p->cap_pinned) {
+		if (p->h_pinned) cudaFreeHost(p->h_pinned);
+		p->h_pinned = NULL;
+		p->cap_pinned = 0;
+		SXS_CK(cudaMallocHost(&p->h_pinned, need));
+		p->cap_pinned = need;
+	}
+	double *h3 = (double *)p->h_pinned;
+	unsigned int *hrows = (unsigned int *)(h3 + 3 * (size_t)nout);
+	SXS_CK(cudaMemcpy(h3, p->d_out3, sizeof(double) * 3 * (size_t)nout, cudaMemcpyDeviceToHost));
 	SXS_CK(cudaMemcpy(hrows, p->d_rows_sorted, sizeof(unsigned int) * (size_t)nvalid, cudaMemcpyDeviceToHost));
 	for (long long i = 0; i < nvalid; i++) {
 		const unsigned int r = hrows[i];
-		scores[r] = h3[3 * i];
-		c1[r] = h3[3 * i + 1];
-		c2[r] = h3[3 * i + 2];
+		scores[r] = h3[r];
+		c1[r] = h3[(size_t)nout + r];
+		c2[r] = h3[2 * (size_t)nout + r];
 	}
-	free(h3);
-	free(hrows);
 	return 0;
 }
 

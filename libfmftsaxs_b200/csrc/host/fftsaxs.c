@@ -144,11 +144,16 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	CHECK_PTR(per_z);
 	const long long cell5 = (long long)nb * nb * N * N * N;
 	long long total = 0;
-	for (long long i = 0; i < nout; i++) {
-		long long v = idx32 != NULL ? (long long)idx32[i] : idx64[i];
-		if (v >= 0 && v / cell5 < znum) {
-			per_z[v / cell5]++;
-			total++;
+	if (ndev == 1) {
+		/* one device takes the whole z table: no need to look at the list on the host */
+		per_z[0] = total = nout;
+	} else {
+		for (long long i = 0; i < nout; i++) {
+			long long v = idx32 != NULL ? (long long)idx32[i] : idx64[i];
+			if (v >= 0 && v / cell5 < znum) {
+				per_z[v / cell5]++;
+				total++;
+			}
 		}
 	}
 	int nz_used = 0;
@@ -157,6 +162,9 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	}
 	if (ndev > nz_used) {
 		ndev = nz_used > 0 ? nz_used : 1;
+	}
+	if (ndev == 1) {
+		per_z[0] = 0; /* the single shard below spans [0, znum) regardless of the histogram */
 	}
 
 	struct shard_job jobs[SXS_MAX_DEV];
