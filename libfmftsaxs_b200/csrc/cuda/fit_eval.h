@@ -72,16 +72,10 @@ SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, doubl
 	double q_prev = -1.0;
 	double up = 0.0, down = 0.0;
 
-	/* the six terms of node i+1 are requested before node i is processed: the row comes from L2/HBM and the
-	 * loop-carried chain would otherwise expose the load latency at every node */
-	double nvv = xvv, nvd = xvd, nvw = xvw, ndd = xdd, ndw = xdw, nww = xww;
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
-		xvv = nvv; xvd = nvd; xvw = nvw; xdd = ndd; xdw = ndw; xww = nww;
-		if (i + 1 < ctx->qnum) {
-			SXS_LOAD6(ctx, i + 1, nvv, nvd, nvw, ndd, ndw, nww);
-		}
 		G = c1_cube * exp(corr * q_cur * q_cur);
+		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
 		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 		const double tan = (in - in_prev) / (q_cur - q_prev);
 		const double buf = in - tan * q_cur;
@@ -118,16 +112,12 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 	double score = 0.0;
 	const double c1_cube = c1 * c1 * c1;
 
-	double nvv = xvv, nvd = xvd, nvw = xvw, ndd = xdd, ndw = xdw, nww = xww;
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
-		xvv = nvv; xvd = nvd; xvw = nvw; xdd = ndd; xdw = ndw; xww = nww;
-		if (i + 1 < ctx->qnum) {
-			SXS_LOAD6(ctx, i + 1, nvv, nvd, nvw, ndd, ndw, nww);
-		}
 		G = c1_cube * exp(corr * q_cur * q_cur);
 		G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q_cur * q_cur);
 
+		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
 
 		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 		const double in_der_c1 = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);
