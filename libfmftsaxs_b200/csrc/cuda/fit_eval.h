@@ -40,10 +40,13 @@ enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 /* The six scaled terms of node q.  With SXS_ROWMAJOR_VEC (CUDA build, point-major rows x[q*6 + c],
  * 16-byte aligned) they come in as three 16-byte loads; the values and their use are identical. */
 #if defined(SXS_ROWMAJOR_VEC) && defined(__CUDA_ARCH__)
+#ifndef SXS_XLD
+#define SXS_XLD(p) (*(p))
+#endif
 #define SXS_LOAD6(ctx, q, vv, vd, vw, dd, dw, ww)                                       \
 	do {                                                                               \
 		const double2 *r_ = reinterpret_cast<const double2 *>((ctx)->x + (long)(q) * 6); \
-		const double2 p0_ = r_[0], p1_ = r_[1], p2_ = r_[2];                             \
+		const double2 p0_ = SXS_XLD(r_), p1_ = SXS_XLD(r_ + 1), p2_ = SXS_XLD(r_ + 2);   \
 		vv = p0_.x * (ctx)->scale; vd = p0_.y * (ctx)->scale;                            \
 		vw = p1_.x * (ctx)->scale; dd = p1_.y * (ctx)->scale;                            \
 		dw = p2_.x * (ctx)->scale; ww = p2_.y * (ctx)->scale;                            \

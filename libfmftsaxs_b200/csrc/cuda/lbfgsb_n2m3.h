@@ -33,8 +33,12 @@
  * instructions (330 KB), and the divergent lanes of a warp then stall on instruction-cache misses
  * (ncu: 63 % of warp cycles in "no instruction"); the objective evaluation stays inlined. */
 #ifdef __CUDACC__
+#ifndef LB_FN
 #define LB_FN __host__ __device__ __noinline__
+#endif
+#ifndef LB_NOUNROLL
 #define LB_NOUNROLL _Pragma("unroll 1")
+#endif
 #else
 #define LB_FN static
 #define LB_NOUNROLL

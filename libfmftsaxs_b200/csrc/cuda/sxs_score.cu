@@ -413,6 +413,72 @@ k_translate(int L, int qnum, int nz, const int *__restrict__ slab_flag, const do
 	}
 }
 
+/* Tiled form of k_translate (the one launched).  A block owns one (b2, q, c) and the pair of orders
+ * (m, L - m) — together L + 2 rows of N outputs, so that every block has the same number of outputs — keeps
+ * the ligand rows Bt[b2][q][c][m, m..L][0..N) of those two orders in shared memory, and walks over the z steps of
+ * the launch: per z it stages the two T^m blocks (rows l, columns l1 >= m) and writes the (L + 2) * N
+ * translated coefficients.  Bt is read from HBM once per launch instead of once per z (the flat kernel's
+ * 10.5 GB of DRAM reads per 64 z at L = 15, profiles/r1c_ncu_traffic.json); the summation order over l1 is
+ * the same as in k_translate. */
+__global__ void __launch_bounds__(288)
+k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, const double2 *__restrict__ T,
+                  const double2 *__restrict__ Bt, double2 *__restrict__ St)
+{
+	extern __shared__ double2 s_tile[];
+	const int nb = L + 1, N = 2 * L + 1, ML = sxs_ml_count(L);
+	const int ma = blockIdx.x, mb = L - (int)blockIdx.x;
+	const int nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
+	const int q = blockIdx.y / 3, c = blockIdx.y % 3, b2 = blockIdx.z;
+	const int nrow = nla + nlb, nout = nrow * N;
+	const int mla = sxs_ml_index(L, ma, ma), mlb = sxs_ml_index(L, mb, mb);
+	double2 *sB = s_tile;            /* [nrow][N] */
+	double2 *sT = s_tile + nout;     /* [nla][nla] then [nlb][nlb] */
+
+	const double2 *bsrc = Bt + (((size_t)b2 * qnum + q) * 3 + c) * ML * N;
+	for (int e = threadIdx.x; e < nla * N; e += blockDim.x) {
+		sB[e] = bsrc[(size_t)mla * N + e];
+	}
+	for (int e = threadIdx.x; e < nlb * N; e += blockDim.x) {
+		sB[nla * N + e] = bsrc[(size_t)mlb * N + e];
+	}
+	for (int zl = 0; zl < nz; zl++) {
+		if (!slab_flag[zl * nb + b2]) {
+			continue;
+		}
+		__syncthreads();
+		const double2 *tsrc = T + ((size_t)zl * qnum + q) * nb * nb * nb;
+		for (int e = threadIdx.x; e < nla * nla; e += blockDim.x) {
+			const int r = e / nla, j = e - r * nla;
+			sT[e] = tsrc[((size_t)ma * nb + ma + r) * nb + ma + j];
+		}
+		for (int e = threadIdx.x; e < nlb * nlb; e += blockDim.x) {
+			const int r = e / nlb, j = e - r * nlb;
+			sT[nla * nla + e] = tsrc[((size_t)mb * nb + mb + r) * nb + mb + j];
+		}
+		__syncthreads();
+		double2 *dst = St + ((((size_t)zl * nb + b2) * qnum + q) * 3 + c) * ML * N;
+		for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+			const int r = o / N, g = o - r * N;
+			const double2 *trow, *bcol;
+			int n, mlrow;
+			if (r < nla) {
+				trow = sT + r * nla; bcol = sB + g; n = nla; mlrow = mla + r;
+			} else {
+				trow = sT + nla * nla + (r - nla) * nlb; bcol = sB + nla * N + g; n = nlb; mlrow = mlb + (r - nla);
+			}
+			double re = 0.0, im = 0.0;
+			for (int j = 0; j < n; j++) {
+				const double2 t = trow[j];
+				const double2 b = bcol[j * N];
+				/* conj(t) * b */
+				re += t.x * b.x + t.y * b.y;
+				im += t.x * b.y - t.y * b.x;
+			}
+			dst[(size_t)mlrow * N + g] = make_double2(re, im);
+		}
+	}
+}
+
 /* ----------------------------------------------------- pose list handling */
 
 #define SXS_KEY_NONE 0xFFFFFFFFFFFFFFFFull
@@ -857,7 +923,19 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		SXS_CK_LAUNCH(); launches++;
 		k_tmatrix<<<grid_for((size_t)zspan * Q * nb * nb * nb, 256), 256, 0, st>>>(L, Q, zspan, d_zlist, p->d_dsymb, p->d_bessel, p->d_T);
 		SXS_CK_LAUNCH(); launches++;
-		k_translate<<<grid_for(slab_elems * nb * zspan, 256, 148u * 64u), 256, 0, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		if (getenv("SXS_TRANSLATE_FLAT") != NULL) { /* tuning only: the untiled kernel */
+			k_translate<<<grid_for(slab_elems * nb * zspan, 256, 148u * 64u), 256, 0, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		} else {
+			const int npair = (L + 2) / 2, rows = L + 2;
+			const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
+			int iters = (rows * N + 287) / 288;
+			int threads = 32 * ((rows * N + 32 * iters - 1) / (32 * iters));
+			if (threads > 288) threads = 288;
+			if (shm_t > 48 * 1024) {
+				SXS_CK(cudaFuncSetAttribute(k_translate_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+			}
+			k_translate_tiled<<<dim3(npair, 3 * Q, nb), threads, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		}
 		SXS_CK_LAUNCH(); launches++;
 		timer_end(p, 1, st);
 		nslabs_total += (long long)zspan * nb;
