@@ -27,6 +27,23 @@ void sxs_ft_file2euler_file(const char *eu_path, const char *ft_path, const char
  * (a2, g2 reflected with the truncated pi, round-half-away, carry instead of modulo). */
 int sxs_euler_to_index(const struct sxs_euler *euler, int z_index, int L);
 
+/* In-memory hand-off replacing the Euler text file between sxs_ft_file2euler_file (src/index.c:77-121) and
+ * the read-back / snapping loop of tools/correlate.c:202-251, with identical results: every row goes through
+ * sxs_ft2euler, the six numbers are quantised exactly as the "% .3f" text round trip quantises them, the
+ * row is kept when its z matches zvals[j] within 0.001, and its flat index is sxs_euler_to_index(.., j, L).
+ * rot_id[i], trans[3*i..] = rotation index and translation of ft row i.  For each kept row k (input order):
+ * index[k], ft_id[k] = rot_id, order[k] = i (the serial number counts every row).  Arrays need room for n
+ * entries.  Rows are converted by `nthreads` host threads (<= 0: one per online core, at most 64).
+ * Returns the number of kept rows. */
+long long sxs_ft_rows_to_indices(int *index, int *ft_id, int *order, const int *rot_id, const double *trans,
+                                 long long n, const struct mol_matrix3_list *rots, struct mol_vector3 *ref_lig,
+                                 const double *zvals, int znum, int L, int nthreads);
+/* same with 64-bit flat indices (needed from L = 20 on, see sxs_compute_saxs_scores64) */
+long long sxs_ft_rows_to_indices64(long long *index, int *ft_id, int *order, const int *rot_id, const double *trans,
+                                   long long n, const struct mol_matrix3_list *rots, struct mol_vector3 *ref_lig,
+                                   const double *zvals, int znum, int L, int nthreads);
+long long sxs_euler_to_index64(const struct sxs_euler *euler, int z_index, int L);
+
 #ifdef __cplusplus
 }
 #endif

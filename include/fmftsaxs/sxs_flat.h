@@ -39,6 +39,12 @@ void sxs_flat_fitted_profile(const double *coef, int qnum, int L, const double *
                              const double *qvals, double *in, double *err, double *out3);
 /* sxs_ft2euler: tv[3], rm[9] row-major, ref_lig[3] -> out6 = z, b1, g1, a2, b2, g2 */
 void sxs_flat_ft2euler(const double *tv, const double *rm, const double *ref_lig, double *out6);
+/* sxs_ft_rows_to_indices64 with the rotation set as rot_mats[nrot][9] (row-major) and ref_lig[3]; returns kept rows */
+long long sxs_flat_ft_rows_to_indices(long long *index, int *ft_id, int *order, const int *rot_id, const double *trans,
+                                      long long n, const double *rot_mats, int nrot, const double *ref_lig,
+                                      const double *zvals, int znum, int L, int nthreads);
+/* sxs_ft_file2euler_file with ref_lig[3] */
+void sxs_flat_ft_file2euler_file(const char *eu_path, const char *ft_path, const char *rm_path, const double *ref_lig);
 /* sxs_euler_to_index on Euler rows euler[n][6] with explicit z indices */
 void sxs_flat_euler_to_index(const double *euler, const int *z_index, int n, int L, int *index);
 /* host tables, for inspection: generate_d_array, sxs_wigner_3j, sxs_sbessel */

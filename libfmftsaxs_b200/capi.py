@@ -201,6 +201,29 @@ def euler_to_index(euler, z_index, L):
     return out
 
 
+def ft_rows_to_indices(rot_id, trans, rot_mats, ref_lig, zvals, L, nthreads=0):
+    """in-memory ft rows -> (flat index int64, ft id, serial number) of the rows on the z table
+    (include/fmftsaxs/index.h: sxs_ft_rows_to_indices64)"""
+    rot_id = np.ascontiguousarray(rot_id, dtype=np.int32)
+    trans = _c(trans).reshape(-1, 3)
+    rot_mats = _c(rot_mats).reshape(-1, 9)
+    zvals = _c(zvals)
+    n = len(rot_id)
+    index = np.zeros(n, dtype=np.int64)
+    ft_id = np.zeros(n, dtype=np.int32)
+    order = np.zeros(n, dtype=np.int32)
+    f = lib().sxs_flat_ft_rows_to_indices
+    f.restype = C.c_longlong
+    kept = f(index.ctypes.data_as(_llp), ft_id.ctypes.data_as(_ip), order.ctypes.data_as(_ip), rot_id.ctypes.data_as(_ip),
+             dptr(trans), C.c_longlong(n), dptr(rot_mats), C.c_int(len(rot_mats)), dptr(_c(ref_lig)), dptr(zvals),
+             C.c_int(len(zvals)), C.c_int(L), C.c_int(nthreads))
+    return index[:kept], ft_id[:kept], order[:kept]
+
+
+def ft_file2euler_file(eu_path, ft_path, rm_path, ref_lig):
+    lib().sxs_flat_ft_file2euler_file(str(eu_path).encode(), str(ft_path).encode(), str(rm_path).encode(), dptr(_c(ref_lig)))
+
+
 def wigner_d(L, beta):
     out = np.zeros((L + 1, 2 * L + 1, 2 * L + 1))
     lib().sxs_flat_wigner_d(C.c_int(L), C.c_double(beta), dptr(out))

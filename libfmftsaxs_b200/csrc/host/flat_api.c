@@ -221,6 +221,32 @@ void sxs_flat_euler_to_index(const double *euler, const int *z_index, int n, int
 	}
 }
 
+long long sxs_flat_ft_rows_to_indices(long long *index, int *ft_id, int *order, const int *rot_id, const double *trans,
+                                      long long n, const double *rot_mats, int nrot, const double *ref_lig,
+                                      const double *zvals, int znum, int L, int nthreads)
+{
+	struct mol_matrix3_list rots;
+	rots.size = (size_t)nrot;
+	rots.members = (struct mol_matrix3 *)malloc(sizeof(struct mol_matrix3) * (size_t)(nrot > 0 ? nrot : 1));
+	CHECK_PTR(rots.members);
+	for (int i = 0; i < nrot; i++) {
+		const double *m = rot_mats + 9 * (size_t)i;
+		struct mol_matrix3 r = {m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]};
+		rots.members[i] = r;
+	}
+	struct mol_vector3 rl = {ref_lig[0], ref_lig[1], ref_lig[2]};
+	const long long kept = sxs_ft_rows_to_indices64(index, ft_id, order, rot_id, trans, n, &rots, &rl, zvals, znum, L,
+	                                                nthreads);
+	free(rots.members);
+	return kept;
+}
+
+void sxs_flat_ft_file2euler_file(const char *eu_path, const char *ft_path, const char *rm_path, const double *ref_lig)
+{
+	struct mol_vector3 rl = {ref_lig[0], ref_lig[1], ref_lig[2]};
+	sxs_ft_file2euler_file(eu_path, ft_path, rm_path, &rl);
+}
+
 void sxs_flat_wigner_d(int L, double beta, double *out)
 {
 	struct d_array *d = generate_d_array(L, beta);

@@ -117,3 +117,20 @@ int sxs_euler_to_index(const struct sxs_euler *euler, int z_index, int L)
 	id = id + (int)(round(g2 / a_step));
 	return id;
 }
+
+long long sxs_euler_to_index64(const struct sxs_euler *euler, int z_index, int L)
+{
+	const long long nbeta = L + 1, n = 2 * L + 1;
+	const double b_step = M_PI / L;
+	const double a_step = 2.0 * M_PI / n;
+	const double a2 = 2 * M_PI - euler->a2;
+	const double g2 = 2 * M_PI - euler->g2;
+
+	long long id = z_index * nbeta;
+	id = (id + (int)(round(euler->b1 / b_step))) * nbeta;
+	id = (id + (int)(round(euler->b2 / b_step))) * n;
+	id = (id + (int)(round(a2 / a_step))) * n;
+	id = (id + (int)(round(euler->g1 / a_step))) * n;
+	id = id + (int)(round(g2 / a_step));
+	return id;
+}

@@ -182,6 +182,59 @@ def test_workload_indices_follow_correlate_snapping(capi):
     assert np.array_equal(got.astype(np.int64), t)
 
 
+def _random_ft_case(rng, nrot, nrows):
+    qn = rng.normal(size=(nrot, 4))
+    qn /= np.linalg.norm(qn, axis=1)[:, None]
+    w, x, y, z = qn.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                  1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w),
+                  1 - 2 * (x * x + y * y)], 1)
+    rot_id = rng.integers(0, nrot, nrows).astype(np.int32)
+    u = rng.normal(size=(nrows, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    ref_lig = np.array([3.0, -2.0, 1.5])
+    dist = rng.uniform(-2.0, 90.0, nrows)          # some rows fall off the 1..80 table on both sides
+    trans = u * dist[:, None] - ref_lig
+    return R, rot_id, trans, ref_lig
+
+
+def test_ft_rows_in_memory_equals_the_euler_file_route(capi, tmp_path):
+    """sxs_ft_rows_to_indices == sxs_ft_file2euler_file + the read-back/snapping loop of
+    tools/correlate.c:202-251 on the same rows (3-decimal text quantisation, rows off the z table dropped, serial
+    numbers counting every row), and the Euler text equals the compiled reference's byte for byte."""
+    rng = np.random.default_rng(11)
+    L, nrot, nrows = 15, 500, 6000
+    R, rot_id, trans, ref_lig = _random_ft_case(rng, nrot, nrows)
+    zvals = np.arange(1.0, 80.001, 1.0)
+    ft, rm, eu = tmp_path / "ft.000.00", tmp_path / "rot.prm", tmp_path / "euler.txt"
+    with open(ft, "w") as f:
+        for i in range(nrows):
+            f.write("%d %.17g %.17g %.17g 0.0 0 0.0 0.0 0.0 0.0\n" % (rot_id[i], *trans[i]))
+    with open(rm, "w") as f:
+        for i in range(nrot):
+            f.write(" ".join("%.17g" % v for v in R[i]) + "\n")
+    capi.ft_file2euler_file(eu, ft, rm, ref_lig)
+    rows = np.loadtxt(eu)
+    assert rows.shape == (nrows, 7)
+    # the tool's loop: keep rows whose z is on the table, index from the quantised angles
+    zi = np.full(nrows, -1)
+    for j, zv in enumerate(zvals):
+        zi[(zv > rows[:, 1] - 0.001) & (zv < rows[:, 1] + 0.001)] = j
+    keep = zi >= 0
+    want_index = capi.euler_to_index(rows[keep, 1:], zi[keep].astype(np.int32), L).astype(np.int64)
+    for nthreads in (1, 4):
+        index, ft_id, order = capi.ft_rows_to_indices(rot_id, trans, R, ref_lig, zvals, L, nthreads=nthreads)
+        assert 0 < len(index) < nrows                       # both kept and dropped rows occur
+        assert np.array_equal(order, np.flatnonzero(keep))
+        assert np.array_equal(ft_id, rot_id[keep])
+        assert np.array_equal(index, want_index)
+    if refso.available():
+        eu_ref = tmp_path / "euler_ref.txt"
+        v = (ctypes.c_double * 3)(*ref_lig)
+        refso.lib().sxs_ft_file2euler_file(str(eu_ref).encode(), str(ft).encode(), str(rm).encode(), v)
+        assert open(eu_ref, "rb").read() == open(eu, "rb").read()
+
+
 # ------------------------------------------------------------------ C ABI
 
 def test_c_abi_exports_every_declared_symbol(capi):
