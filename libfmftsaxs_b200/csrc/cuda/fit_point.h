@@ -35,13 +35,16 @@ SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const doub
 	ctx.qvals = qvals;
 	ctx.qnum = qnum;
 	ctx.mult = mult;
+	ctx.rq = NULL; /* the serial form divides in the loop */
 	ctx.scale = 1.0;
 	ctx.scale = sxs_fit_rescale(&ctx, peak);
 
 	struct lb_state st;
 	lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
+	const double sum_a0 = sxs_fit_sum_a0(a, qnum);
+	(void)sum_a0;
 	while (lb_step(&st, 1e-5) == LB_NEED_EVAL) {
-		sxs_fit_eval(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+		SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 	}
 	*score = sqrt(st.f);
 	*c1 = st.x[1];

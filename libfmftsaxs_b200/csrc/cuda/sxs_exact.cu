@@ -8,8 +8,9 @@
  *   k_self_terms     six self cross terms of one molecule (src/min_saxs.c:437-499)
  *   k_profile        I(q) of one molecule (src/profile.c:186-233)
  *
- * K4 roofline: FP64 pipe.  Per objective evaluation a thread does qnum*(~190 flops + 2 exp) and re-reads
- * its 6*qnum cross terms (coalesced across the warp, L2-resident); 7-13 evaluations per fit on real data.
+ * K4: per objective evaluation a thread makes one pass over its 6*qnum cross terms (one exp per node,
+ * sxs_fit_eval_fused); 7-13 evaluations per fit on real data, ~20 on the synthetic bench workload.  Build
+ * with -DSXS_FIT_EVAL_EXACT for the reference's two-pass objective (bit-identical to it up to exp()).
  */
 #include <math.h>
 
@@ -17,6 +18,13 @@
 
 #define SXS_HD __host__ __device__ __forceinline__
 #define SXS_ROWMAJOR_VEC 1
+#ifndef SXS_FIT_EVAL_EXACT
+#define SXS_FIT_EVAL_FUSED 1   /* [B200] 1.12 M fits: 66.8 ms two-pass, 52.5 ms one-pass */
+#define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory: 51.8 ms */
+#endif
+#ifndef SXS_XLD
+#define SXS_XLD __ldcs         /* cross-term rows are streamed (evict-first): 49.5 ms */
+#endif
 #include "fit_point.h"
 
 #define SXS_FIT_MAXQ 512
@@ -29,6 +37,22 @@
 #ifndef SXS_FIT_WARPSYNC
 #define SXS_FIT_BLOCKSYNC 1 /* [B200] 1.12 M fits: 88 ms with warp-level rounds, 67 ms with block-level rounds */
 #endif
+
+/* part B of the optimiser runs when NUM/DEN of the block's running fits wait for it (or none can evaluate) */
+#ifndef SXS_FIT_BATCH_NUM
+#define SXS_FIT_BATCH_NUM 3
+#endif
+#ifndef SXS_FIT_BATCH_DEN
+#define SXS_FIT_BATCH_DEN 4
+#endif
+
+__device__ __forceinline__ void fit_store(const struct lb_state *st, double *__restrict__ res, long long p)
+{
+	res[p * 4 + 0] = sqrt(st->f);
+	res[p * 4 + 1] = st->x[1];
+	res[p * 4 + 2] = st->x[2];
+	res[p * 4 + 3] = (double)st->nfgv;
+}
 
 /* K4.  X is point-major: the 6*qnum cross terms of point p are the contiguous row X[p*6*qnum + q*6 + k]
  * (2.4 KB at Q = 50), read with 16-byte loads.
@@ -44,26 +68,57 @@ __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {
-	extern __shared__ double s_tab[]; /* [6*qnum] moments, then [qnum] q grid */
+	extern __shared__ double s_tab[]; /* [6*qnum] moments, [qnum] q grid, [qnum] reciprocal node spacings */
 	double *s_a = s_tab;
 	double *s_q = s_tab + 6 * qnum;
+	double *s_rq = s_tab + 7 * qnum;
 	for (int i = threadIdx.x; i < 6 * qnum; i += blockDim.x) {
 		s_a[i] = a[i];
 	}
 	for (int i = threadIdx.x; i < qnum; i += blockDim.x) {
 		s_q[i] = qvals[i];
+		s_rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
 	}
 	__syncthreads();
 
 	struct lb_state st;
 	struct sxs_fit_ctx ctx;
 	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
-	ctx.x = X; ctx.scale = 1.0;
+	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq;
+	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
+	(void)sum_a0;
 	long long p = -1;
-	bool have = false, drained = false;
+	bool drained = false;
+	/* what this lane's fit waits for */
+	enum { FREE = 0, EVALUATED, WANT_EVAL, WANT_B };
+	int mode = FREE;
 
 	for (;;) {
-		if (!have && !drained) {
+		/* (1) line-search turn (part A of the optimiser, short) for every lane that has a fresh f, g */
+		if (mode == EVALUATED) {
+			const int r = lb_step_a(&st);
+			mode = (r == LB_NEED_EVAL) ? WANT_EVAL : (r == LB_NEED_B) ? WANT_B : FREE;
+			if (r == LB_DONE) {
+				fit_store(&st, res, p);
+			}
+		}
+		/* (2) iteration boundary (part B: BFGS update, Cauchy point, subspace step; ~17x the instructions of
+		 * an evaluation) is run by the whole block at once, and only when enough of its lanes wait for it:
+		 * a lane that has finished its line search idles through a few evaluation rounds instead of
+		 * dragging its warp through part B with a third of the lanes active. */
+		const int n_b = __syncthreads_count(mode == WANT_B);
+		const int n_e = __syncthreads_count(mode == WANT_EVAL);
+		if (n_b > 0 && (n_e == 0 || n_b * SXS_FIT_BATCH_DEN >= (n_b + n_e) * SXS_FIT_BATCH_NUM)) {
+			if (mode == WANT_B) {
+				const int r = lb_step_b(&st, 1e-5);
+				mode = (r == LB_NEED_EVAL) ? WANT_EVAL : FREE;
+				if (r == LB_DONE) {
+					fit_store(&st, res, p);
+				}
+			}
+		}
+		/* (3) free lanes take the next point from the ticket counter */
+		if (mode == FREE && !drained) {
 			p = (long long)atomicAdd(ticket, 1ull);
 			if (p < npts) {
 				ctx.x = X + (size_t)p * 6 * qnum;
@@ -72,38 +127,23 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 					ctx.scale = sxs_fit_rescale(&ctx, peak);
 				}
 				lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
-				have = true;
+				const int r = lb_step_a(&st); /* projects the start into the box and asks for f, g there */
+				mode = (r == LB_NEED_EVAL) ? WANT_EVAL : (r == LB_NEED_B) ? WANT_B : FREE;
+				if (r == LB_DONE) {
+					fit_store(&st, res, p);
+				}
 			} else {
 				drained = true;
 			}
 		}
-#ifdef SXS_FIT_BLOCKSYNC
-		/* all warps of the block enter the optimiser step, and then the evaluation, together: they share the
-		 * instruction stream, which is what the instruction cache of the SM needs (5 700 SASS instructions) */
-		if (!__syncthreads_or(have ? 1 : 0)) {
+		/* (4) all warps of the block enter the evaluation together: they share the instruction stream, which is
+		 * what the instruction cache of the SM needs (5 700 SASS instructions in total) */
+		if (!__syncthreads_or(mode != FREE)) {
 			break;
 		}
-#else
-		if (__ballot_sync(0xffffffffu, have) == 0u) {
-			break;
-		}
-#endif
-		if (have) {
-			if (lb_step(&st, 1e-5) == LB_DONE) {
-				res[p * 4 + 0] = sqrt(st.f);
-				res[p * 4 + 1] = st.x[1];
-				res[p * 4 + 2] = st.x[2];
-				res[p * 4 + 3] = (double)st.nfgv;
-				have = false;
-			}
-		}
-#ifdef SXS_FIT_BLOCKSYNC
-		__syncthreads();
-#else
-		__syncwarp();
-#endif
-		if (have) {
-			sxs_fit_eval(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+		if (mode == WANT_EVAL) {
+			SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+			mode = EVALUATED;
 		}
 		__syncwarp();
 	}
@@ -122,7 +162,7 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	int dev = 0, sms = 148, per_sm = 4;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const size_t shm = sizeof(double) * 7 * qnum;
+	const size_t shm = sizeof(double) * 8 * qnum;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
 	if (per_sm < 1) per_sm = 1;
 	if (getenv("SXS_FIT_BLOCKS_PER_SM")) { /* tuning only */
@@ -190,7 +230,7 @@ __global__ void k_fit_eval(const double *__restrict__ cross, const double *__res
 	ctx.x = cross; /* point-major row x[q*6 + k] */
 	ctx.stride = 1;
 	ctx.qstride = 6;
-	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0;
+	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = NULL;
 	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
 	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);
 }

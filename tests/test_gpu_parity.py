@@ -93,9 +93,13 @@ def test_fit_kernel_against_reference_lbfgsb(G, FC):
     assert relmax(got[:, 0], want[:, 0]) < TOL
     assert relmax(got[:, 1], want[:, 1]) < TOL
     assert np.max(np.abs(got[:, 2] - want[:, 2])) < TOL * 4
-    # same trajectory: the number of objective evaluations agrees for nearly every fit (device exp() and
-    # glibc exp() differ in the last ulp now and then, which can move a line search by one evaluation)
-    assert np.mean(got[:, 3] == want[:, 3]) > 0.99
+    # same trajectory for most fits: the kernel's one-pass objective (fit_eval.h, sxs_fit_eval_fused) equals the
+    # reference's two-pass value up to rounding, which moves a line search by one evaluation now and then
+    # (95.7 % identical counts here; 99.7 % with -DSXS_FIT_EVAL_EXACT, where only exp() differs in the last ulp).
+    # The optimiser itself is bit-identical to the reference's (tests/test_cpu_host.py, fit headers on the host).
+    # Fits that end in a line search at the noise floor of f can differ by tens of evaluations and still agree in
+    # (chi, c1, c2) to 1e-8 (measured on the host build of the same headers).
+    assert np.mean(got[:, 3] == want[:, 3]) > 0.9
 
 
 def test_cross_terms_z40(G, FC):
