@@ -61,6 +61,18 @@ enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 	} while (0)
 #endif
 
+/* optional software prefetch of the row a few nodes ahead (device builds only; tuning knob) */
+#if defined(SXS_PREFETCH_AHEAD) && defined(__CUDA_ARCH__)
+#define SXS_PREFETCH_ROW(ctx, i)                                                                          \
+	do {                                                                                                 \
+		if ((i) + SXS_PREFETCH_AHEAD < (ctx)->qnum) {                                                    \
+			asm volatile(SXS_PREFETCH_OP " [%0];" ::"l"((ctx)->x + (long)((i) + SXS_PREFETCH_AHEAD) * 6)); \
+		}                                                                                                \
+	} while (0)
+#else
+#define SXS_PREFETCH_ROW(ctx, i) do { } while (0)
+#endif
+
 /* src/min_saxs.c:261-319 */
 SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, double c2)
 {
@@ -187,10 +199,13 @@ SXS_HD void sxs_fit_eval_fused(const struct sxs_fit_ctx *ctx, double sum_a0, dou
 	double d2_prev = xvw - G * xdw + 2.0 * c2 * xww;
 	double q_prev = -1.0;
 
+	/* f's own coefficient sums need no accumulators: sum(-2 buf a1 - 2 tan a2) = -2 up and
+	 * sum(buf^2 a3 + 2 buf tan a4 + tan^2 a5) = down, exactly (scaling by 2 commutes with rounding) */
 	double up = 0.0, down = 0.0;
-	double sp0 = 0.0, sr0 = 0.0, sp1 = 0.0, sr1 = 0.0, sps = 0.0, srs = 0.0;
+	double sp0 = 0.0, sr0 = 0.0, sp1 = 0.0, sr1 = 0.0;
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
+		SXS_PREFETCH_ROW(ctx, i);
 		if (i > 0) {
 			SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
 			G = c1_cube * exp(corr * q_cur * q_cur);
@@ -214,24 +229,23 @@ SXS_HD void sxs_fit_eval_fused(const struct sxs_fit_ctx *ctx, double sum_a0, dou
 		const double a1 = a[i * 6 + 1], a2 = a[i * 6 + 2], a3 = a[i * 6 + 3], a4 = a[i * 6 + 4], a5 = a[i * 6 + 5];
 
 		up += buf * a1 + tan * a2;
-		down += buf * buf * a3 + 2.0 * tan * buf * a4 + tan * tan * a5;
+		down += buf * buf * a3 + 2.0 * buf * tan * a4 + tan * tan * a5;
 
 		sp0 += -b1 * a1 - t1 * a2;
 		sr0 += buf * b1 * a3 + (in * t1 + d1 * tan - 2.0 * tan * t1 * q_cur) * a4 + tan * t1 * a5;
 		sp1 += -b2 * a1 - t2 * a2;
 		sr1 += buf * b2 * a3 + (in * t2 + d2 * tan - 2.0 * tan * t2 * q_cur) * a4 + tan * t2 * a5;
-		sps += -2.0 * buf * a1 - 2.0 * tan * a2;
-		srs += buf * buf * a3 + 2.0 * buf * tan * a4 + tan * tan * a5;
 
 		in_prev = in;
 		d1_prev = d1;
 		d2_prev = d2;
 		q_prev = q_cur;
 	}
+	(void)q_prev;
 	const double k = up / down;
 	*g0 = 2.0 * k * (sp0 + k * sr0);
 	*g1 = 2.0 * k * (sp1 + k * sr1);
-	*f = sum_a0 + k * (sps + k * srs);
+	*f = sum_a0 + k * (-2.0 * up + k * down);
 }
 
 /* the evaluation the fit uses */
