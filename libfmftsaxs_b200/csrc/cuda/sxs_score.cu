@@ -584,7 +584,14 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
  * same 496-byte row, served by L1/L2.
  * X[(p - p0)*6*qnum + q*6 + k] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108);
  * point-major rows, so that K4 streams one contiguous 6*qnum row per fit. */
-__global__ void __launch_bounds__(256)
+/* [B200] 1.12 M points: 256x1 39.3 ms, 256x3 (80 regs, spills) 40.9, 128x4 38.4, 128x5 45.1, 64x8 38.4, 512x1 41.1 */
+#ifndef SXS_CROSS_THREADS
+#define SXS_CROSS_THREADS 128
+#endif
+#ifndef SXS_CROSS_MINBLOCKS
+#define SXS_CROSS_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(SXS_CROSS_THREADS, SXS_CROSS_MINBLOCKS)
 k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0,
         const double2 *__restrict__ At, const double2 *__restrict__ St, const double2 *__restrict__ tw,
         const double *__restrict__ cst, double *__restrict__ X)
@@ -943,9 +950,9 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		for (long long c0 = g0; c0 < g1; c0 += chunk_max) {
 			const long long c1e = (c0 + chunk_max < g1) ? c0 + chunk_max : g1;
 			const long long cnt = c1e - c0;
-			dim3 grid((unsigned)((cnt + 255) / 256), Q);
+			dim3 grid((unsigned)((cnt + SXS_CROSS_THREADS - 1) / SXS_CROSS_THREADS), Q);
 			timer_begin(p, 2, st);
-			k_cross<<<grid, 256, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, z_first, p->d_At, p->d_St, p->d_tw,
+			k_cross<<<grid, SXS_CROSS_THREADS, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, z_first, p->d_At, p->d_St, p->d_tw,
 			                                                 p->d_const, p->d_X);
 			SXS_CK_LAUNCH(); launches++;
 			timer_end(p, 2, st);
