@@ -322,10 +322,14 @@ def run_product(args):
         # K4: per objective evaluation and q node 147 flops + 2 exp at 20 flops, optimiser logic not counted
         fit_flops = evals_total * Q * (147 + 2 * 20)
 
+        traffic = ncu_traffic(n)
+
         def roof(name, flops_per_step, ms_total, launches):
             ach = flops_per_step * args.steps / (ms_total * 1e-3) / 1e12 if ms_total > 0 else None
+            key = name.split(" ")[0]
             return {"kernel": name, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": (ach / fp64_peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / fp64_peak) if ach else None, "traffic": traffic.get(key), "peak_source": peak_src,
+                    "traffic_source": TRAFFIC_FILE if key in traffic else None,
                     "flops_per_launch": flops_per_step / max(1, launches // args.steps),
                     "avg_launch_ms": ms_total / max(1, launches), "ms_per_step": ms_total / args.steps}
 
@@ -350,6 +354,7 @@ def run_product(args):
                 "fit_evaluations": {"mean": nfg_mean, "p50": int(np.searchsorted(np.cumsum(hist), 0.5 * hist.sum())),
                                     "p99": int(np.searchsorted(np.cumsum(hist), 0.99 * hist.sum())),
                                     "max_bin": int(np.flatnonzero(hist).max()) if hist.sum() else 0},
+                "pose_list": pose_list_stats(idx, L),
                 "roofline": roofline, "roofline_second_kernel": roofline2, "cpu_baseline": cpu,
                 "resident_equals_host_path": same}
         print(json.dumps(line))
@@ -357,6 +362,30 @@ def run_product(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def pose_list_stats(idx, L):
+    """the distributions throughput depends on: rows per (z, beta1, beta2) cell"""
+    N = 2 * L + 1
+    _, counts = np.unique(idx.astype(np.int64) // N ** 3, return_counts=True)
+    return {"cells": int(len(counts)), "rows_per_cell_mean": float(counts.mean()),
+            "rows_per_cell_p50": int(np.percentile(counts, 50)), "rows_per_cell_p99": int(np.percentile(counts, 99)),
+            "rows_per_cell_max": int(counts.max())}
+
+
+TRAFFIC_FILE = "profiles/r1d_ncu_traffic.json"
+
+
+def ncu_traffic(poses_per_gpu):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels, from the committed ncu
+    launch list of this very command; only quoted when the workload is the one that was profiled"""
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), TRAFFIC_FILE)))
+    except OSError:
+        return {}
+    if t.get("workload") != WORKLOAD or t.get("poses_per_gpu") != poses_per_gpu:
+        return {}
+    return {k: v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"] for k, v in t["kernels"].items()}
 
 
 def cpu_baseline(w, args):
