@@ -345,7 +345,8 @@ def run_product(args):
                 "config": {"workload": WORKLOAD, "poses_per_gpu": int(n), "distinct_grid_points": int(stats["points"]),
                            "L": L, "qnum": Q, "z_steps": int(len(zvals)), "rec_atoms": len(w["rec"]["res"]),
                            "lig_atoms": len(w["lig"]["res"]),
-                           "l2_policy": "inputs larger than L2 (rotated tables 324 MB + translated slabs %.1f GB per step)" % (stats["slabs"] * Q * 3 * ML * N * 16 / 1e9)},
+                           "l2_policy": "inputs larger than L2 (rotated tables %.0f MB + translated slabs %.1f GB per step)"
+                                        % (2 * (L + 1) * Q * 3 * ML * N * 16 / 1e6, stats["slabs"] * Q * 3 * ML * N * 16 / 1e9)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_steps, "api": "sxs_compute_saxs_scores (flat adapter), pinned host buffers"},
@@ -410,6 +411,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, help="pose-list/molecule configuration of libfmftsaxs_b200.workload.CONFIGS "
+                    "(default: BASELINE config 3; config 4 is a separate measurement, see profiles/)")
     ap.add_argument("--nrot", type=int, default=None, help="override rotations per z (default 70000)")
     ap.add_argument("--nz", type=int, default=None, help="override number of z steps (default 64)")
     ap.add_argument("--cpu-slabs", type=int, default=1)
@@ -417,6 +420,9 @@ def main():
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-slabs-per-proc", type=int, default=1)
     args = ap.parse_args()
+    if args.workload:
+        global WORKLOAD
+        WORKLOAD = args.workload
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
