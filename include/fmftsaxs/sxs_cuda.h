@@ -92,6 +92,13 @@ int sxs_cuda_plan_fit_evaluations(sxs_cuda_plan *plan, long long *hist64);
 int sxs_cuda_plan_set_profiling(sxs_cuda_plan *plan, int on);
 int sxs_cuda_plan_kernel_times(sxs_cuda_plan *plan, double *ms5, long long *launches5);
 
+/* Dense scan (the reference's skip = 0 mode of src/fftsaxs.c:867-872 computes every point of every cell
+ * but reports only listed rows): every grid point (b1, b2, a2, g1, g2) of the z steps [z_lo, z_hi) is scored and the
+ * k points of lowest chi are returned, chi ascending: flat 64-bit index (-1 = empty slot), chi, c1, c2.  Host arrays
+ * of length k. */
+int sxs_cuda_plan_scan_topk(sxs_cuda_plan *plan, int z_lo, int z_hi, int k, long long *index, double *scores,
+                            double *c1, double *c2);
+
 /* Debug/stage access for parity tests: cross terms of the listed poses, cross[(row*6 + k)*qnum + q],
  * before the peak rescale (what fill_const/fill_var leave in the profile, src/fftsaxs.c:52-108). */
 int sxs_cuda_plan_cross_terms_i32(sxs_cuda_plan *plan, const int *index, long long nout, double *cross);

@@ -326,6 +326,15 @@ class Plan:
         f = lib().sxs_cuda_plan_score_dev_i64 if i64 else lib().sxs_cuda_plan_score_dev_i32
         _check(f(self._h, d_index_ptr, n, z_lo, z_hi, d_scores_ptr, d_c1_ptr, d_c2_ptr, stream_ptr), "score_device")
 
+    def scan_topk(self, k, z_lo=0, z_hi=None):
+        """score every grid point of the z steps [z_lo, z_hi) and return the k best (index int64, chi, c1, c2)"""
+        z_hi = self.znum if z_hi is None else z_hi
+        idx = np.zeros(k, dtype=np.int64)
+        s, c1, c2 = np.zeros(k), np.zeros(k), np.zeros(k)
+        _check(lib().sxs_cuda_plan_scan_topk(self._h, C.c_int(z_lo), C.c_int(z_hi), C.c_int(k), idx.ctypes.data_as(_llp),
+                                             dptr(s), dptr(c1), dptr(c2)), "scan_topk")
+        return idx, s, c1, c2
+
     def cross_terms(self, index):
         idx = np.ascontiguousarray(index, dtype=np.int32)
         out = np.zeros((len(idx), 6, len(self.qvals)))

@@ -1005,6 +1005,149 @@ extern "C" int sxs_cuda_plan_score_dev_i64(sxs_cuda_plan *p, const long long *d_
 	return score_core<long long>(p, d_index, nout, z_lo, z_hi, d_scores, d_c1, d_c2, NULL, NULL, (cudaStream_t)stream, NULL);
 }
 
+/* ------------------------------------------------------------ dense scan with top-k */
+
+__global__ void k_scan_indices(long long base, long long n, long long *__restrict__ idx)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		idx[i] = base + i;
+	}
+}
+
+/* merge keys: [0, k) the running best, [k, k + n) the new chunk; NaN sorts last */
+__global__ void k_scan_keys(const double *__restrict__ best, int k, const double *__restrict__ chunk, long long n,
+                            double *__restrict__ keys, unsigned int *__restrict__ vals)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= k + n) {
+		return;
+	}
+	double v = i < k ? best[i] : chunk[i - k];
+	if (!(v == v)) {
+		v = INFINITY;
+	}
+	keys[i] = v;
+	vals[i] = (unsigned int)i;
+}
+
+__global__ void k_scan_take(const unsigned int *__restrict__ vals_sorted, const double *__restrict__ keys_sorted, int k,
+                            const long long *__restrict__ old_idx, const double *__restrict__ old3,
+                            const long long *__restrict__ new_idx, const double *__restrict__ s,
+                            const double *__restrict__ c1, const double *__restrict__ c2, long long *__restrict__ out_idx,
+                            double *__restrict__ out3)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= k) {
+		return;
+	}
+	const unsigned int src = vals_sorted[j];
+	if (src < (unsigned int)k) {
+		out_idx[j] = old_idx[src];
+		out3[j] = old3[src]; out3[k + j] = old3[k + src]; out3[2 * k + j] = old3[2 * k + src];
+	} else {
+		const unsigned int r = src - (unsigned int)k;
+		out_idx[j] = isinf(keys_sorted[j]) ? -1 : new_idx[r];
+		out3[j] = keys_sorted[j]; out3[k + j] = c1[r]; out3[2 * k + j] = c2[r];
+	}
+}
+
+/* Every grid point (b1, b2, a2, g1, g2) of the z steps [z_lo, z_hi) is scored, one (z, b1) row of cells per pass,
+ * and the k points of lowest chi are kept.  The reference's skip = 0 mode computes the same dense set per cell
+ * (src/fftsaxs.c:867-872) but can only report rows of a list; this returns the best rows themselves.
+ * Out: flat 64-bit indices (-1 when fewer than k points exist), chi ascending, c1, c2. */
+extern "C" int sxs_cuda_plan_scan_topk(sxs_cuda_plan *p, int z_lo, int z_hi, int k, long long *index, double *scores,
+                                       double *c1, double *c2)
+{
+	SXS_CK(cudaSetDevice(p->device));
+	if (k < 1 || k > (1 << 24)) {
+		sxs_cuda_set_error("scan_topk: k out of range");
+		return -1;
+	}
+	if (z_lo < 0) z_lo = 0;
+	if (z_hi > p->znum) z_hi = p->znum;
+	const long long nb = p->nb, N = p->N;
+	const long long per_row = nb * N * N * N; /* points of one (z, b1): all b2, a2, g1, g2 */
+	cudaStream_t st = 0;
+	long long *d_idx = NULL, *d_best_idx[2] = {NULL, NULL};
+	double *d_out = NULL, *d_best3[2] = {NULL, NULL}, *d_keys = NULL, *d_keys_sorted = NULL;
+	unsigned int *d_vals = NULL, *d_vals_sorted = NULL;
+	void *d_tmp = NULL;
+	size_t tmp_bytes = 0;
+	const long long m = per_row + k;
+	int rc = -1;
+	cudaError_t e = cudaSuccess;
+#define TK(call) do { if (e == cudaSuccess) e = (call); } while (0)
+	TK(cudaMalloc(&d_idx, sizeof(long long) * per_row));
+	TK(cudaMalloc(&d_out, sizeof(double) * 3 * per_row));
+	TK(cudaMalloc(&d_keys, sizeof(double) * m));
+	TK(cudaMalloc(&d_keys_sorted, sizeof(double) * m));
+	TK(cudaMalloc(&d_vals, sizeof(unsigned int) * m));
+	TK(cudaMalloc(&d_vals_sorted, sizeof(unsigned int) * m));
+	for (int b = 0; b < 2; b++) {
+		TK(cudaMalloc(&d_best_idx[b], sizeof(long long) * k));
+		TK(cudaMalloc(&d_best3[b], sizeof(double) * 3 * k));
+	}
+	if (e == cudaSuccess) {
+		e = cub::DeviceRadixSort::SortPairs(NULL, tmp_bytes, d_keys, d_keys_sorted, d_vals, d_vals_sorted, (int)m);
+	}
+	TK(cudaMalloc(&d_tmp, tmp_bytes));
+	if (e == cudaSuccess) {
+		/* running best starts as k empty slots: chi = +inf, index -1 */
+		double *h3 = (double *)malloc(sizeof(double) * 3 * k);
+		long long *hi = (long long *)malloc(sizeof(long long) * k);
+		for (int j = 0; j < k; j++) { h3[j] = INFINITY; h3[k + j] = 0.0; h3[2 * k + j] = 0.0; hi[j] = -1; }
+		TK(cudaMemcpy(d_best3[0], h3, sizeof(double) * 3 * k, cudaMemcpyHostToDevice));
+		TK(cudaMemcpy(d_best_idx[0], hi, sizeof(long long) * k, cudaMemcpyHostToDevice));
+		free(h3); free(hi);
+	}
+	int cur = 0;
+	long long launches = 0, points = 0;
+	if (e == cudaSuccess) {
+		rc = 0;
+		for (int z = z_lo; z < z_hi && rc == 0; z++) {
+			for (int b1 = 0; b1 < nb && rc == 0; b1++) {
+				const long long base = ((long long)z * nb + b1) * per_row;
+				k_scan_indices<<<(unsigned)((per_row + 255) / 256), 256, 0, st>>>(base, per_row, d_idx);
+				rc = score_core<long long>(p, d_idx, per_row, z, z + 1, d_out, d_out + per_row, d_out + 2 * per_row, NULL,
+				                           NULL, st, NULL);
+				if (rc != 0) break;
+				launches += p->stats[2] + 4;
+				points += per_row;
+				k_scan_keys<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_best3[cur], k, d_out, per_row, d_keys, d_vals);
+				e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_sorted, d_vals, d_vals_sorted, (int)m, 0,
+				                                    64, st);
+				if (e != cudaSuccess) { rc = -1; break; }
+				k_scan_take<<<(k + 255) / 256, 256, 0, st>>>(d_vals_sorted, d_keys_sorted, k, d_best_idx[cur], d_best3[cur],
+				                                            d_idx, d_out, d_out + per_row, d_out + 2 * per_row,
+				                                            d_best_idx[cur ^ 1], d_best3[cur ^ 1]);
+				cur ^= 1;
+			}
+		}
+		if (rc == 0) {
+			TK(cudaStreamSynchronize(st));
+			TK(cudaGetLastError());
+			TK(cudaMemcpy(index, d_best_idx[cur], sizeof(long long) * k, cudaMemcpyDeviceToHost));
+			TK(cudaMemcpy(scores, d_best3[cur], sizeof(double) * k, cudaMemcpyDeviceToHost));
+			TK(cudaMemcpy(c1, d_best3[cur] + k, sizeof(double) * k, cudaMemcpyDeviceToHost));
+			TK(cudaMemcpy(c2, d_best3[cur] + 2 * k, sizeof(double) * k, cudaMemcpyDeviceToHost));
+		}
+	}
+#undef TK
+	if (e != cudaSuccess) {
+		sxs_cuda_set_error("scan_topk: %s", cudaGetErrorString(e));
+		rc = -1;
+	}
+	cudaFree(d_idx); cudaFree(d_out); cudaFree(d_keys); cudaFree(d_keys_sorted); cudaFree(d_vals); cudaFree(d_vals_sorted);
+	cudaFree(d_tmp);
+	for (int b = 0; b < 2; b++) { cudaFree(d_best_idx[b]); cudaFree(d_best3[b]); }
+	if (rc == 0) {
+		p->stats[0] = points;
+		p->stats[2] = launches;
+	}
+	return rc;
+}
+
 template <typename IndexT>
 static int score_host(sxs_cuda_plan *p, const IndexT *index, long long nout, int z_lo, int z_hi, double *scores,
                       double *c1, double *c2)

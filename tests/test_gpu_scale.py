@@ -101,3 +101,47 @@ def test_properties_on_bench_workload():
     flat = capi.scores(idx, A, B, a, scal, q, w["zvals"], L)
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(base, flat))
     plan.close()
+    # tight workspace budgets: 2 z steps per translated group, ~1000 points per cross-term chunk -> same bits
+    old = {k: os.environ.get(k) for k in ("SXS_CUDA_ST_GB", "SXS_CUDA_X_GB")}
+    os.environ["SXS_CUDA_ST_GB"], os.environ["SXS_CUDA_X_GB"] = "0.4", "0.002"
+    try:
+        small = capi.Plan(L, q)
+        small.set_molecules(A, B)
+        small.set_experiment(a, scal[1], scal[2])
+        small.set_translations(w["zvals"])
+        tight = small.score(idx)
+        assert small.stats()["groups"] >= 3 and small.stats()["launches"] > 30
+        small.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(base, tight))
+
+
+def test_dense_scan_topk():
+    """every grid point of one z step (16 x 16 cells x 31^3 = 7.6 M points) is scored on the device and
+    the best 64 come back; they are what the list API gives for the same indices, and no sampled point beats them"""
+    G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+    q, L = G["qvals"], int(G["L"])
+    nb, N = L + 1, 2 * L + 1
+    plan = capi.Plan(L, q)
+    plan.set_molecules(G["rec_coef"], G["lig_coef"])
+    plan.set_experiment(G["a"], G["scal"][1], G["scal"][2])
+    plan.set_translations(np.array([38.0, 40.0]))
+    k = 64
+    idx, s, c1, c2 = plan.scan_topk(k, z_lo=1, z_hi=2)
+    per_z = nb * nb * N ** 3
+    assert plan.stats()["points"] == per_z
+    assert (idx >= per_z).all() and (idx < 2 * per_z).all() and len(np.unique(idx)) == k
+    assert np.all(np.diff(s) >= 0) and np.isfinite(s).all()
+    ls, lc1, lc2 = plan.score(idx)
+    assert np.array_equal(ls, s) and np.array_equal(lc1, c1) and np.array_equal(lc2, c2)
+    sample = np.random.default_rng(5).integers(per_z, 2 * per_z, 200000)
+    ss, _, _ = plan.score(sample)
+    better = sample[ss < s[-1]]
+    assert np.isin(better, idx).all()
+    assert ss.min() >= s[0]
+    plan.close()
