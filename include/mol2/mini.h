@@ -76,6 +76,9 @@ struct mol_atom_group *mol_atom_group_create(size_t natoms);
 void mol_atom_group_free(struct mol_atom_group *ag);
 struct mol_atom_group *mol_atom_group_join(const struct mol_atom_group *a, const struct mol_atom_group *b);
 void mol_atom_group_translate(struct mol_atom_group *ag, const struct mol_vector3 *t);
+/* dst->coords[i] = R * src->coords[i] + t (libmol2 transform.h; used by tools/score_ft_naive.c:161-164) */
+void mol_atom_group_move_in_copy(const struct mol_atom_group *src, struct mol_atom_group *dst,
+                                 const struct mol_matrix3 *rotation, const struct mol_vector3 *translation);
 void centroid(struct mol_vector3 *c, const struct mol_atom_group *ag);
 void center_of_extrema(struct mol_vector3 *c, const struct mol_atom_group *ag);
 

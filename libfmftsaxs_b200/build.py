@@ -19,7 +19,7 @@ LIB = os.path.join(PKG, "libfmftsaxs.so")
 HOST_SRC = ["sfbessel.c", "saxs_utils.c", "tables.c", "form_factor_table.c", "pdb2spf.c", "profile.c",
             "min_saxs.c", "index.c", "index_rows.c", "fftsaxs.c", "mol2_mini.c", "flat_api.c"]
 CUDA_SRC = [("sxs_score.cu", []), ("sxs_expand.cu", []), ("sxs_exact.cu", ["-fmad=false"])]
-TOOLS = ["correlate", "single_saxs"]
+TOOLS = ["correlate", "single_saxs", "score_ft_naive"]
 
 INCS = ["-I" + os.path.join(REPO, "include"), "-I" + os.path.join(REPO, "include", "fmftsaxs"),
         "-I" + os.path.join(CSRC, "host"), "-I" + os.path.join(CSRC, "cuda")]

@@ -156,6 +156,18 @@ void mol_atom_group_translate(struct mol_atom_group *ag, const struct mol_vector
 	}
 }
 
+void mol_atom_group_move_in_copy(const struct mol_atom_group *src, struct mol_atom_group *dst,
+                                 const struct mol_matrix3 *r, const struct mol_vector3 *t)
+{
+	const size_t n = src->natoms < dst->natoms ? src->natoms : dst->natoms;
+	for (size_t i = 0; i < n; i++) {
+		const struct mol_vector3 v = src->coords[i];
+		dst->coords[i].X = r->m11 * v.X + r->m12 * v.Y + r->m13 * v.Z + t->X;
+		dst->coords[i].Y = r->m21 * v.X + r->m22 * v.Y + r->m23 * v.Z + t->Y;
+		dst->coords[i].Z = r->m31 * v.X + r->m32 * v.Y + r->m33 * v.Z + t->Z;
+	}
+}
+
 void centroid(struct mol_vector3 *c, const struct mol_atom_group *ag)
 {
 	struct mol_vector3 s = {0.0, 0.0, 0.0};

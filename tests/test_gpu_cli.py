@@ -89,3 +89,35 @@ def test_single_saxs_cli_matches_reference_tool(files):
         a, b = np.loadtxt(d / "p_ours"), np.loadtxt(d / "p_ref")
         assert a.shape == b.shape == (50, 3)
         assert np.max(np.abs(a[:, 1] / b[:, 1] - 1)) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_score_ft_naive")), reason="compiled reference tools not present")
+def test_score_ft_naive_cli_matches_reference_tool_and_the_fft_path(files):
+    """SURVEY 8f-3, tools/score_ft_naive.c: the real-space validator (pose built atom by atom, K1 + self terms + K4 per
+    pose) gives the reference tool's rows, and agrees with `correlate` as far as the truncation at L = 15 allows"""
+    d = files
+    rows = open(d / "ft.000").read().splitlines()[:10]
+    with open(d / "ft.naive", "w") as f:
+        f.write("\n".join(rows) + "\n")
+    common = [MAP, PRM, str(d / "ft.naive"), str(d / "rot.prm"), str(d / "rec.pdb"), str(d / "lig.pdb"), str(d / "exp.dat"), "15"]
+    for exe, out in ((os.path.join(BIN, "score_ft_naive"), "naive_ours"), (os.path.join(REF, "ref_score_ft_naive"), "naive_ref")):
+        wd = d / ("wd_" + out)
+        os.makedirs(wd, exist_ok=True)
+        r = subprocess.run([exe] + common + [str(d / out)], cwd=wd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:]
+    assert open(d / "wd_naive_ours" / "euler_list").read() == open(d / "wd_naive_ref" / "euler_list").read()
+    ours, ref = np.loadtxt(d / "naive_ours"), np.loadtxt(d / "naive_ref")
+    assert ours.shape == ref.shape == (10, 4)
+    assert np.array_equal(ours[:, 0], ref[:, 0])
+    assert np.max(np.abs(ours[:, 1:] - ref[:, 1:])) <= 1.001e-3      # "%.3f" columns
+    # against the FFT path on the rows that lie on its z table
+    subprocess.run([os.path.join(BIN, "correlate")] + common + [str(d / "eul_n"), str(d / "out_n")], check=True,
+                   stdout=subprocess.DEVNULL, timeout=600)
+    fft = {int(l.split("\t")[0]): [float(x) for x in l.split("\t")[2:]] for l in open(d / "out_n").read().splitlines()}
+    assert len(fft) >= 3
+    dev = np.array([[ours[i, 1] / fft[i][0] - 1, ours[i, 2] - fft[i][1], ours[i, 3] - fft[i][2]] for i in fft])
+    print("naive vs FFT path on %d rows: max rel dchi %.3g, max dc1 %.3g, max dc2 %.3g" % (len(fft), np.abs(dev[:, 0]).max(),
+          np.abs(dev[:, 1]).max(), np.abs(dev[:, 2]).max()))
+    # different hydration weights (joined vs separate molecules) and different truncations: same physics, not same digits
+    assert np.abs(dev[:, 0]).max() < 0.25
