@@ -415,7 +415,7 @@ def main():
                     "(default: BASELINE config 3; config 4 is a separate measurement, see profiles/)")
     ap.add_argument("--nrot", type=int, default=None, help="override rotations per z (default 70000)")
     ap.add_argument("--nz", type=int, default=None, help="override number of z steps (default 64)")
-    ap.add_argument("--cpu-slabs", type=int, default=1)
+    ap.add_argument("--cpu-slabs", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-slabs-per-proc", type=int, default=1)

@@ -33,6 +33,10 @@ extern "C" void sxs_cuda_set_error(const char *fmt, ...);
 __host__ __device__ inline int sxs_ml_count(int L) { return (L + 1) * (L + 2) / 2; }
 __host__ __device__ inline int sxs_ml_index(int L, int m, int l) { return m * (L + 1) - m * (m - 1) / 2 + (l - m); }
 
+/* Rows of the rotated/translated tables hold N = 2L+1 complex values and are padded to a multiple of 8 (128 bytes),
+ * so that the 8 values g = 8k .. 8k+7 — one "band" — are exactly one cache line. */
+__host__ __device__ inline int sxs_row_pad(int N) { return (N + 7) & ~7; }
+
 /* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
 
 /* K4: one fit per point.  x: point-major cross terms, x[p*6*qnum + q*6 + k]; res[p*4] = chi, c1, c2,

@@ -11,7 +11,7 @@
  * BEFORE the l-contraction, once per molecule and independent of z:
  *   At[b1][q][c][m,l][g1] = sum_m1 w^(m1 g1) d^l_{m m1}(b1)      A^c_{l m1}(q)        (k_rotate, receptor)
  *   Bt[b2][q][c][m,l][g2] = sum_m2 w^(m2 g2) d^l_{m m2}(b2) conj(B^c_{l m2}(q))       (k_rotate, ligand)
- *   St[z,b2][q][c][m,l][g2] = sum_l1 conj(T^m_{l l1}(q z)) Bt[b2][q][c][m,l1][g2]      (k_translate)
+ *   St[z,b2][q][c][m,l][g2] = sum_l1 conj(T^m_{l l1}(q z)) Bt[b2][q][c][m,l1][g2]      (k_translate_tiled)
  * and what is left per listed pose (z, b1, b2, a2, g1, g2) is the alpha transform of a length-(L+1) dot:
  *   F_k = Re sum_m w^(m a2) sum_{l>=|m|} At^{c}[m,l,g1] St^{c'}[m,l,g2]                  (k_cross)
  * Only m >= 0 is evaluated: the m <-> -m terms are complex conjugates of each other (A_{l,-m} =
@@ -22,7 +22,7 @@
  * (truncated pi, src/fftsaxs.c:536-548).
  *
  * Pose list handling (replaces the O(cells*nout) mask scans, src/fftsaxs.c:716-733,850-872,922-936):
- * keys (z,b2,b1,g1,g2,a2) are radix-sorted on the device, duplicates collapse into distinct grid
+ * keys (z, b2, b1, g2 / 8, g1, g2 % 8, a2) are radix-sorted on the device, duplicates collapse into distinct grid
  * points, each point is fitted once and scattered back to every row that named it.
  */
 #include <cub/cub.cuh>
@@ -72,7 +72,7 @@ struct sxs_cuda_plan {
 	/* molecules */
 	double2 *d_coefA, *d_coefB;
 	double *d_const;  /* [6][qnum] */
-	double2 *d_At, *d_Bt; /* [beta][q][c][ml][g] */
+	double2 *d_At, *d_Bt; /* [beta][q][c][ml][g], rows padded to sxs_row_pad(N) */
 	int have_molecules;
 	/* experiment */
 	double *d_a;
@@ -83,7 +83,7 @@ struct sxs_cuda_plan {
 	int znum;
 	/* workspace (grow-only) */
 	double2 *d_T;  size_t cap_T;   /* [zg][q][m][l][l1] */
-	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g] */
+	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g], rows padded like At */
 	double *d_X;   size_t cap_X;   /* [chunk][q][6] point-major rows */
 	unsigned long long *d_ticket;
 	double *d_res; size_t cap_res; /* [points][4] */
@@ -101,7 +101,7 @@ struct sxs_cuda_plan {
 	size_t budget_St, budget_X;
 	long long stats[5];
 	/* optional per-kernel-class device timing (CUDA events on the launching stream) */
-	int profiling;
+	int profiling, events_ready;
 	cudaEvent_t ev[SXS_NTIMERS][2 * SXS_MAX_TIMED];
 	int ev_used[SXS_NTIMERS];
 	double ms[SXS_NTIMERS];
@@ -191,7 +191,7 @@ extern "C" sxs_cuda_plan *sxs_cuda_plan_create(int device, int L, int qnum, cons
 	const size_t nds = (size_t)p->nb * p->nb * p->nb * p->N;
 	const size_t ndw = (size_t)p->nb * p->nb * p->N * p->N;
 	const size_t ncoef = (size_t)3 * qnum * p->nb * p->nb;
-	const size_t nrot = (size_t)p->nb * qnum * 3 * p->ML * p->N;
+	const size_t nrot = (size_t)p->nb * qnum * 3 * p->ML * sxs_row_pad(p->N);
 	cudaError_t e = cudaSuccess;
 #define PC(call) do { if (e == cudaSuccess) e = (call); } while (0)
 	PC(cudaMalloc(&p->d_qvals, sizeof(double) * qnum));
@@ -254,18 +254,16 @@ extern "C" int sxs_cuda_plan_stats(const sxs_cuda_plan *p, long long *stats5)
 extern "C" int sxs_cuda_plan_set_profiling(sxs_cuda_plan *p, int on)
 {
 	SXS_CK(cudaSetDevice(p->device));
-	if (on && !p->profiling) {
+	if (on && !p->events_ready) {
 		for (int w = 0; w < SXS_NTIMERS; w++) {
 			for (int i = 0; i < 2 * SXS_MAX_TIMED; i++) {
 				SXS_CK(cudaEventCreate(&p->ev[w][i]));
 			}
-			p->ev_used[w] = 0;
 		}
+		p->events_ready = 1; /* events stay allocated once created */
 	}
-	p->profiling = on ? 1 : p->profiling; /* events stay allocated once created */
-	if (!on) {
-		for (int w = 0; w < SXS_NTIMERS; w++) p->ev_used[w] = 0;
-	}
+	p->profiling = on ? 1 : 0;
+	for (int w = 0; w < SXS_NTIMERS; w++) p->ev_used[w] = 0;
 	return 0;
 }
 
@@ -283,21 +281,26 @@ extern "C" int sxs_cuda_plan_kernel_times(sxs_cuda_plan *p, double *ms5, long lo
 /* ------------------------------------------------ K2a: rotation + gamma DFT */
 
 /* out[b][q][c][ml][g] = sum_{m1=-l..l} w^(m1 g) d^l_{m m1}(beta_b) coef^c[q][l,m1]   (conj(coef) for the ligand).
- * One thread per output element, g fastest: the d and coef operands are warp-uniform broadcasts. */
+ * One thread per output element, g fastest (rows of NP = sxs_row_pad(N) values, the padding is zero): the d and
+ * coef operands are warp-uniform broadcasts. */
 __global__ void __launch_bounds__(256)
 k_rotate(int L, int qnum, const double *__restrict__ dwig, const double2 *__restrict__ coef,
          const double2 *__restrict__ tw, int conjugate, double2 *__restrict__ out)
 {
 	extern __shared__ double2 s_tw[];
-	const int N = 2 * L + 1, nb = L + 1, ML = sxs_ml_count(L), lm_n = nb * nb;
+	const int N = 2 * L + 1, NP = sxs_row_pad(N), nb = L + 1, ML = sxs_ml_count(L), lm_n = nb * nb;
 	for (int i = threadIdx.x; i < N; i += blockDim.x) {
 		s_tw[i] = tw[i];
 	}
 	__syncthreads();
-	const size_t total = (size_t)nb * qnum * 3 * ML * N;
+	const size_t total = (size_t)nb * qnum * 3 * ML * NP;
 	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-		const int g = (int)(e % N);
-		size_t rest = e / N;
+		const int g = (int)(e % NP);
+		size_t rest = e / NP;
+		if (g >= N) {
+			out[e] = make_double2(0.0, 0.0);
+			continue;
+		}
 		const int ml = (int)(rest % ML); rest /= ML;
 		const int c = (int)(rest % 3); rest /= 3;
 		const int q = (int)(rest % qnum);
@@ -373,59 +376,19 @@ k_tmatrix(int L, int qnum, int nz, const int *__restrict__ zlist, const double *
 	}
 }
 
-/* St[slab][q][c][ml(m,l)][g] = sum_{l1=m..L} conj(T^m_{l l1}) Bt[b2][q][c][ml(m,l1)][g], slab = zl*nb + b2.
- * Slabs whose (z, b2) holds no listed pose are skipped.  One thread per output element, g fastest. */
-__global__ void __launch_bounds__(256)
-k_translate(int L, int qnum, int nz, const int *__restrict__ slab_flag, const double2 *__restrict__ T,
-            const double2 *__restrict__ Bt, double2 *__restrict__ St)
-{
-	const int nb = L + 1, N = 2 * L + 1, ML = sxs_ml_count(L);
-	const size_t per_slab = (size_t)qnum * 3 * ML * N;
-	const size_t total = (size_t)nz * nb * per_slab;
-	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-		const int slab = (int)(e / per_slab);
-		if (!slab_flag[slab]) {
-			continue;
-		}
-		size_t rest = e % per_slab;
-		const int g = (int)(rest % N); rest /= N;
-		const int ml = (int)(rest % ML); rest /= ML;
-		const int c = (int)(rest % 3);
-		const int q = (int)(rest / 3);
-		const int zl = slab / nb, b2 = slab % nb;
-		int m = 0, off = ml;
-		while (off >= nb - m) {
-			off -= nb - m;
-			m++;
-		}
-		const int l = m + off;
-		const double2 *trow = T + (((size_t)zl * qnum + q) * nb + m) * nb * nb + (size_t)l * nb; /* index by l1 */
-		const double2 *brow = Bt + ((((size_t)b2 * qnum + q) * 3 + c) * ML + sxs_ml_index(L, m, m)) * N + g;
-		double re = 0.0, im = 0.0;
-		for (int l1 = m; l1 <= L; l1++) {
-			const double2 t = trow[l1];
-			const double2 b = brow[(size_t)(l1 - m) * N];
-			/* conj(t) * b */
-			re += t.x * b.x + t.y * b.y;
-			im += t.x * b.y - t.y * b.x;
-		}
-		St[e] = make_double2(re, im);
-	}
-}
-
-/* Tiled form of k_translate (the one launched).  A block owns one (b2, q, c) and the pair of orders
+/* K2c.  St[slab][q][c][ml(m,l)][g] = sum_{l1=m..L} conj(T^m_{l l1}) Bt[b2][q][c][ml(m,l1)][g], slab = zl*nb + b2;
+ * slabs whose (z, b2) holds no listed pose are skipped.  A block owns one (b2, q, c) and the pair of orders
  * (m, L - m) — together L + 2 rows of N outputs, so that every block has the same number of outputs — keeps
  * the ligand rows Bt[b2][q][c][m, m..L][0..N) of those two orders in shared memory, and walks over the z steps of
  * the launch: per z it stages the two T^m blocks (rows l, columns l1 >= m) and writes the (L + 2) * N
- * translated coefficients.  Bt is read from HBM once per launch instead of once per z (the flat kernel's
- * 10.5 GB of DRAM reads per 64 z at L = 15, profiles/r1c_ncu_traffic.json); the summation order over l1 is
- * the same as in k_translate. */
+ * translated coefficients.  Bt is read from HBM once per launch instead of once per z (an untiled
+ * one-thread-per-output form read 10.5 GB per 64 z at L = 15, profiles/r1c_ncu_traffic.json); l1 ascends. */
 __global__ void __launch_bounds__(288)
 k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, const double2 *__restrict__ T,
                   const double2 *__restrict__ Bt, double2 *__restrict__ St)
 {
 	extern __shared__ double2 s_tile[];
-	const int nb = L + 1, N = 2 * L + 1, ML = sxs_ml_count(L);
+	const int nb = L + 1, N = 2 * L + 1, NP = sxs_row_pad(N), ML = sxs_ml_count(L);
 	const int ma = blockIdx.x, mb = L - (int)blockIdx.x;
 	const int nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
 	const int q = blockIdx.y / 3, c = blockIdx.y % 3, b2 = blockIdx.z;
@@ -434,12 +397,14 @@ k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, co
 	double2 *sB = s_tile;            /* [nrow][N] */
 	double2 *sT = s_tile + nout;     /* [nla][nla] then [nlb][nlb] */
 
-	const double2 *bsrc = Bt + (((size_t)b2 * qnum + q) * 3 + c) * ML * N;
+	const double2 *bsrc = Bt + (((size_t)b2 * qnum + q) * 3 + c) * ML * NP;
 	for (int e = threadIdx.x; e < nla * N; e += blockDim.x) {
-		sB[e] = bsrc[(size_t)mla * N + e];
+		const int r = e / N, g = e - r * N;
+		sB[e] = bsrc[(size_t)(mla + r) * NP + g];
 	}
 	for (int e = threadIdx.x; e < nlb * N; e += blockDim.x) {
-		sB[nla * N + e] = bsrc[(size_t)mlb * N + e];
+		const int r = e / N, g = e - r * N;
+		sB[nla * N + e] = bsrc[(size_t)(mlb + r) * NP + g];
 	}
 	for (int zl = 0; zl < nz; zl++) {
 		if (!slab_flag[zl * nb + b2]) {
@@ -456,7 +421,7 @@ k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, co
 			sT[nla * nla + e] = tsrc[((size_t)mb * nb + mb + r) * nb + mb + j];
 		}
 		__syncthreads();
-		double2 *dst = St + ((((size_t)zl * nb + b2) * qnum + q) * 3 + c) * ML * N;
+		double2 *dst = St + ((((size_t)zl * nb + b2) * qnum + q) * 3 + c) * ML * NP;
 		for (int o = threadIdx.x; o < nout; o += blockDim.x) {
 			const int r = o / N, g = o - r * N;
 			const double2 *trow, *bcol;
@@ -474,7 +439,7 @@ k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, co
 				re += t.x * b.x + t.y * b.y;
 				im += t.x * b.y - t.y * b.x;
 			}
-			dst[(size_t)mlrow * N + g] = make_double2(re, im);
+			dst[(size_t)mlrow * NP + g] = make_double2(re, im);
 		}
 	}
 }
@@ -483,7 +448,11 @@ k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, co
 
 #define SXS_KEY_NONE 0xFFFFFFFFFFFFFFFFull
 
-/* flat index (z,b1,b2,a2,g1,g2 digits, src/index.c:9-29) -> sort key (z,b2,b1,g1,g2,a2) */
+/* flat index (z,b1,b2,a2,g1,g2 digits, src/index.c:9-29) -> sort key (z, b2, b1, g2 / 8, g1, g2 % 8, a2).
+ * Inside a cell the points are ordered by the 128-byte band of their ligand operand first, then by g1: eight
+ * consecutive points (a quarter warp of k_cross) then read ligand values of ONE cache line and receptor values of
+ * neighbouring g1, i.e. one line as well.  With (g1, g2) order a quarter warp's ligand values spread over the
+ * whole row (4 lines).  per_cell = (NP / 8) * N * 8 * N keys per (z, b2, b1). */
 template <typename IndexT>
 __global__ void k_make_keys(const IndexT *__restrict__ index, long long nout, int nb, int N, int z_lo, int z_hi,
                             unsigned long long *__restrict__ keys, unsigned int *__restrict__ rows)
@@ -502,7 +471,8 @@ __global__ void k_make_keys(const IndexT *__restrict__ index, long long nout, in
 		const long long b1 = v % nb;
 		const long long z = v / nb;
 		if (z >= z_lo && z < z_hi) {
-			key = (unsigned long long)((((((z * nb + b2) * nb + b1) * N + g1) * N + g2) * N) + a2);
+			const long long nband = sxs_row_pad(N) / 8;
+			key = (unsigned long long)(((((((z * nb + b2) * nb + b1) * nband + g2 / 8) * N + g1) * 8 + g2 % 8) * N) + a2);
 		}
 	}
 	keys[i] = key;
@@ -578,13 +548,16 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
 	acc.y = fma(a.y, b.x, acc.y);
 }
 
-/* One thread per distinct grid point, one q per blockIdx.y.  Consecutive threads are consecutive in
- * (z, b2, b1, g1, g2, a2) order, so a block mostly works inside one cell: the receptor rows it reads
- * differ only in g1 (nearly warp-uniform) and the ligand rows only in g2 — both 16-byte elements of the
- * same 496-byte row, served by L1/L2.
+/* One thread per distinct grid point, one q per blockIdx.y.  Consecutive threads are consecutive in key order
+ * (k_make_keys), so a block mostly works inside one cell and a quarter warp inside one band of g2: its ligand
+ * operands are 16-byte elements of one 128-byte line, its receptor operands those of a few neighbouring g1 —
+ * served by L1/L2.
  * X[(p - p0)*6*qnum + q*6 + k] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108);
  * point-major rows, so that K4 streams one contiguous 6*qnum row per fit. */
-/* [B200] 1.12 M points: 256x1 39.3 ms, 256x3 (80 regs, spills) 40.9, 128x4 38.4, 128x5 45.1, 64x8 38.4, 512x1 41.1 */
+/* [B200] 1.12 M points, (g1, g2, a2) order, 496-byte rows: 256x1 39.3 ms, 256x3 (80 regs, spills) 40.9, 128x4 38.4,
+ * 128x5 45.1, 64x8 38.4, 512x1 41.1.  Band-major order + 512-byte rows: 128x4 36.1 (L1 data-pipe wavefronts per
+ * 16-byte warp load 6.4 -> 4.2, the minimum: one per quarter warp); + next row requested before the MACs of the
+ * current one: 128x4 35.7, 128x3 35.7, 64x6 35.4, 256x1 36.7. */
 #ifndef SXS_CROSS_THREADS
 #define SXS_CROSS_THREADS 128
 #endif
@@ -607,46 +580,62 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		return;
 	}
 	const int q = blockIdx.y;
+	const int NP = sxs_row_pad(N), nband = NP / 8;
 	unsigned long long key = pkeys[p];
 	const int a2 = (int)(key % N); key /= N;
-	const int g2 = (int)(key % N); key /= N;
+	int g2 = (int)(key % 8); key /= 8;
 	const int g1 = (int)(key % N); key /= N;
+	g2 += 8 * (int)(key % nband); key /= nband;
 	const int b1 = (int)(key % nb); key /= nb;
 	const int b2 = (int)(key % nb);
 	const int z = (int)(key / nb);
 	const int slab = (z - z0) * nb + b2;
 
-	const size_t cstride = (size_t)ML * N;
+	const size_t cstride = (size_t)ML * NP;
 	const double2 *a_ptr = At + (((size_t)b1 * qnum + q) * 3) * cstride + g1;
 	const double2 *s_ptr = St + (((size_t)slab * qnum + q) * 3) * cstride + g2;
 
 	double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
 	int ka = 0; /* (m*a2) mod N */
+	/* one flat loop over the ML (m, l) rows; the six operands of the next row are requested before the nine complex
+	 * MACs of the current one, so that a warp always has a row in flight behind its arithmetic */
+	double2 cvv = {0, 0}, cvd = {0, 0}, cvw = {0, 0}, cdd = {0, 0}, cdw = {0, 0}, cww = {0, 0};
+	double2 av = __ldg(a_ptr), ad = __ldg(a_ptr + cstride), aw = __ldg(a_ptr + 2 * cstride);
+	double2 sv = __ldg(s_ptr), sd = __ldg(s_ptr + cstride), sw = __ldg(s_ptr + 2 * cstride);
+	int m = 0, l = 0;
 	size_t row = 0;
-	for (int m = 0; m <= L; m++) {
-		double2 cvv = {0, 0}, cvd = {0, 0}, cvw = {0, 0}, cdd = {0, 0}, cdw = {0, 0}, cww = {0, 0};
-		for (int l = m; l <= L; l++, row += N) {
-			const double2 av = __ldg(a_ptr + row), ad = __ldg(a_ptr + cstride + row), aw = __ldg(a_ptr + 2 * cstride + row);
-			const double2 sv = __ldg(s_ptr + row), sd = __ldg(s_ptr + cstride + row), sw = __ldg(s_ptr + 2 * cstride + row);
-			cmac(cvv, av, sv);
-			cmac(cvd, av, sd); cmac(cvd, ad, sv);
-			cmac(cvw, av, sw); cmac(cvw, aw, sv);
-			cmac(cdd, ad, sd);
-			cmac(cdw, ad, sw); cmac(cdw, aw, sd);
-			cmac(cww, aw, sw);
+#pragma unroll 2
+	for (int step = 0; step < ML; step++) {
+		row += NP;
+		const size_t nrow = (step + 1 < ML) ? row : 0;
+		const double2 nav = __ldg(a_ptr + nrow), nad = __ldg(a_ptr + cstride + nrow), naw = __ldg(a_ptr + 2 * cstride + nrow);
+		const double2 nsv = __ldg(s_ptr + nrow), nsd = __ldg(s_ptr + cstride + nrow), nsw = __ldg(s_ptr + 2 * cstride + nrow);
+		cmac(cvv, av, sv);
+		cmac(cvd, av, sd); cmac(cvd, ad, sv);
+		cmac(cvw, av, sw); cmac(cvw, aw, sv);
+		cmac(cdd, ad, sd);
+		cmac(cdw, ad, sw); cmac(cdw, aw, sd);
+		cmac(cww, aw, sw);
+		if (l == L) {
+			const double2 w = s_tw[ka];
+			const double fac = (m == 0) ? 1.0 : 2.0;
+			f0 += fac * (w.x * cvv.x - w.y * cvv.y);
+			f1 += fac * (w.x * cvd.x - w.y * cvd.y);
+			f2 += fac * (w.x * cvw.x - w.y * cvw.y);
+			f3 += fac * (w.x * cdd.x - w.y * cdd.y);
+			f4 += fac * (w.x * cdw.x - w.y * cdw.y);
+			f5 += fac * (w.x * cww.x - w.y * cww.y);
+			cvv = cvd = cvw = cdd = cdw = cww = make_double2(0.0, 0.0);
+			ka += a2;
+			if (ka >= N) {
+				ka -= N;
+			}
+			m++;
+			l = m;
+		} else {
+			l++;
 		}
-		const double2 w = s_tw[ka];
-		const double fac = (m == 0) ? 1.0 : 2.0;
-		f0 += fac * (w.x * cvv.x - w.y * cvv.y);
-		f1 += fac * (w.x * cvd.x - w.y * cvd.y);
-		f2 += fac * (w.x * cvw.x - w.y * cvw.y);
-		f3 += fac * (w.x * cdd.x - w.y * cdd.y);
-		f4 += fac * (w.x * cdw.x - w.y * cdw.y);
-		f5 += fac * (w.x * cww.x - w.y * cww.y);
-		ka += a2;
-		if (ka >= N) {
-			ka -= N;
-		}
+		av = nav; ad = nad; aw = naw; sv = nsv; sd = nsd; sw = nsw;
 	}
 	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - p0) * qnum + q) * 6);
 	xo[0] = make_double2(cst[0 * qnum + q] + 2.0 * f0, cst[1 * qnum + q] + 2.0 * f1);
@@ -726,7 +715,7 @@ extern "C" int sxs_cuda_plan_set_molecules(sxs_cuda_plan *p, const double *coefA
 	if (sxs_launch_pair_const((const double *)p->d_coefA, (const double *)p->d_coefB, p->qnum, p->L, p->d_const, 0) != 0) {
 		return -1;
 	}
-	const size_t nrot = (size_t)p->nb * p->qnum * 3 * p->ML * p->N;
+	const size_t nrot = (size_t)p->nb * p->qnum * 3 * p->ML * sxs_row_pad(p->N);
 	const size_t shm = sizeof(double2) * p->N;
 	k_rotate<<<grid_for(nrot, 256), 256, shm>>>(p->L, p->qnum, p->d_dwig, p->d_coefA, p->d_tw, 0, p->d_At);
 	SXS_CK_LAUNCH();
@@ -863,7 +852,8 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	if (np == 0) {
 		return 0;
 	}
-	const unsigned long long per_zb2 = (unsigned long long)nb * N * N * N;
+	const unsigned long long per_cell = (unsigned long long)(sxs_row_pad(N) / 8) * N * 8 * N; /* keys per (z, b2, b1) */
+	const unsigned long long per_zb2 = (unsigned long long)nb * per_cell;
 	const unsigned long long per_z = per_zb2 * nb;
 	k_z_offsets<<<(znum + 2 + 127) / 128, 128, 0, st>>>(p->d_pkeys, np, p->d_keys_sorted, nout, znum, per_z, p->d_zoff);
 	SXS_CK_LAUNCH(); launches++;
@@ -877,7 +867,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	if (ensure(&p->d_res, &p->cap_res, (size_t)np * 4)) return -1;
 
 	/* --- group sizing --- */
-	const size_t slab_elems = (size_t)Q * 3 * ML * N;           /* double2 per (z,b2) slab */
+	const size_t slab_elems = (size_t)Q * 3 * ML * sxs_row_pad(N); /* double2 per (z,b2) slab */
 	const size_t per_z_bytes = slab_elems * nb * sizeof(double2);
 	int zg_max = (int)(p->budget_St / per_z_bytes);
 	if (zg_max < 1) zg_max = 1;
@@ -930,9 +920,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		SXS_CK_LAUNCH(); launches++;
 		k_tmatrix<<<grid_for((size_t)zspan * Q * nb * nb * nb, 256), 256, 0, st>>>(L, Q, zspan, d_zlist, p->d_dsymb, p->d_bessel, p->d_T);
 		SXS_CK_LAUNCH(); launches++;
-		if (getenv("SXS_TRANSLATE_FLAT") != NULL) { /* tuning only: the untiled kernel */
-			k_translate<<<grid_for(slab_elems * nb * zspan, 256, 148u * 64u), 256, 0, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
-		} else {
+		{
 			const int npair = (L + 2) / 2, rows = L + 2;
 			const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
 			int iters = (rows * N + 287) / 288;
