@@ -444,6 +444,116 @@ k_translate_tiled(int L, int qnum, int nz, const int *__restrict__ slab_flag, co
 	}
 }
 
+/* Register-tiled form of the same contraction (the one launched).  Same block ownership and staging as
+ * k_translate_tiled; a thread now produces a 4 x 2 tile — four consecutive rows l of one order and the two columns
+ * g, g + GH (GH = (N + 1) / 2) — so that per l1 it reads two ligand values and four (warp-broadcast) T values from
+ * shared memory for eight complex MACs: 0.75 LDS.128 per complex MAC instead of 2, which is what bounded the
+ * one-output-per-thread form (ncu: shared-memory pipe, 23 % of HBM peak).  Every output sees the same operations in
+ * the same order as before (product, fused multiply-add, add; l1 ascending): St is bit-identical.
+ * [B200] 64 z, every slab: L = 15 8.4 -> 6.9 ms, L = 30 160 -> 136 ms (128 registers: 216 ms; 2-row tiles: 160 ms).
+ * Six FP64 instructions per complex MAC put the FP64-pipe floor at 61 ms for L = 30; the HBM floor (151 GB written)
+ * is 25 ms. */
+#ifndef SXS_TR_ROWS
+#define SXS_TR_ROWS 4
+#endif
+#ifndef SXS_TR_MINBLOCKS
+#define SXS_TR_MINBLOCKS 2 /* 64 registers: at L = 30 (288 threads) three blocks per SM instead of one */
+#endif
+#ifndef SXS_TR_UNROLL
+#define SXS_TR_UNROLL 1
+#endif
+#define SXS_PRAGMA_(x) _Pragma(#x)
+#define SXS_UNROLL(n) SXS_PRAGMA_(unroll n)
+__global__ void __launch_bounds__(512, SXS_TR_MINBLOCKS)
+k_translate_rt(int L, int qnum, int nz, const int *__restrict__ slab_flag, const double2 *__restrict__ T,
+               const double2 *__restrict__ Bt, double2 *__restrict__ St)
+{
+	extern __shared__ double2 s_tile[];
+	const int nb = L + 1, N = 2 * L + 1, NP = sxs_row_pad(N), ML = sxs_ml_count(L), GH = (N + 1) / 2;
+	const int ma = blockIdx.x, mb = L - (int)blockIdx.x;
+	const int nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
+	const int q = blockIdx.y / 3, c = blockIdx.y % 3, b2 = blockIdx.z;
+	const int nrow = nla + nlb, nout = nrow * N;
+	const int mla = sxs_ml_index(L, ma, ma), mlb = sxs_ml_index(L, mb, mb);
+	double2 *sB = s_tile;            /* [nrow][N] */
+	double2 *sT = s_tile + nout;     /* [nla][nla] then [nlb][nlb] */
+
+	const double2 *bsrc = Bt + (((size_t)b2 * qnum + q) * 3 + c) * ML * NP;
+	for (int e = threadIdx.x; e < nla * N; e += blockDim.x) {
+		const int r = e / N, g = e - r * N;
+		sB[e] = bsrc[(size_t)(mla + r) * NP + g];
+	}
+	for (int e = threadIdx.x; e < nlb * N; e += blockDim.x) {
+		const int r = e / N, g = e - r * N;
+		sB[nla * N + e] = bsrc[(size_t)(mlb + r) * NP + g];
+	}
+	/* this thread's tile */
+	const int tiles_a = (nla + SXS_TR_ROWS - 1) / SXS_TR_ROWS, tiles_b = (nlb + SXS_TR_ROWS - 1) / SXS_TR_ROWS;
+	const int tile = threadIdx.x / GH, g0 = threadIdx.x - tile * GH, g1 = g0 + GH;
+	const bool active = tile < tiles_a + tiles_b;
+	const bool in_a = tile < tiles_a;
+	const int n = in_a ? nla : nlb;                               /* rows = columns of this order's T block */
+	const int r0 = SXS_TR_ROWS * (in_a ? tile : tile - tiles_a); /* first row of the tile inside its order */
+	const double2 *tblk = sT + (in_a ? 0 : nla * nla);
+	const double2 *bcol = sB + (in_a ? 0 : nla * N);
+	const int mlrow0 = (in_a ? mla : mlb) + r0;
+	const bool has_g1 = g1 < N;
+	int rr[SXS_TR_ROWS];
+#pragma unroll
+	for (int k = 0; k < SXS_TR_ROWS; k++) {
+		rr[k] = (r0 + k < n) ? r0 + k : n - 1; /* rows past the block repeat the last one and are not stored */
+	}
+
+	for (int zl = 0; zl < nz; zl++) {
+		if (!slab_flag[zl * nb + b2]) {
+			continue;
+		}
+		__syncthreads();
+		const double2 *tsrc = T + ((size_t)zl * qnum + q) * nb * nb * nb;
+		for (int e = threadIdx.x; e < nla * nla; e += blockDim.x) {
+			const int r = e / nla, j = e - r * nla;
+			sT[e] = tsrc[((size_t)ma * nb + ma + r) * nb + ma + j];
+		}
+		for (int e = threadIdx.x; e < nlb * nlb; e += blockDim.x) {
+			const int r = e / nlb, j = e - r * nlb;
+			sT[nla * nla + e] = tsrc[((size_t)mb * nb + mb + r) * nb + mb + j];
+		}
+		__syncthreads();
+		if (!active) {
+			continue;
+		}
+		double re[SXS_TR_ROWS][2], im[SXS_TR_ROWS][2];
+#pragma unroll
+		for (int k = 0; k < SXS_TR_ROWS; k++) {
+			re[k][0] = re[k][1] = im[k][0] = im[k][1] = 0.0;
+		}
+		SXS_UNROLL(SXS_TR_UNROLL)
+		for (int j = 0; j < n; j++) {
+			const double2 bA = bcol[j * N + g0];
+			const double2 bB = has_g1 ? bcol[j * N + g1] : make_double2(0.0, 0.0);
+#pragma unroll
+			for (int k = 0; k < SXS_TR_ROWS; k++) {
+				const double2 t = tblk[rr[k] * n + j];
+				/* conj(t) * b, accumulated as acc + fma(t.x, b.x, t.y * b.y) and acc + fma(t.x, b.y, -(t.y * b.x)) */
+				re[k][0] = __dadd_rn(re[k][0], __fma_rn(t.x, bA.x, __dmul_rn(t.y, bA.y)));
+				im[k][0] = __dadd_rn(im[k][0], __fma_rn(t.x, bA.y, -__dmul_rn(t.y, bA.x)));
+				re[k][1] = __dadd_rn(re[k][1], __fma_rn(t.x, bB.x, __dmul_rn(t.y, bB.y)));
+				im[k][1] = __dadd_rn(im[k][1], __fma_rn(t.x, bB.y, -__dmul_rn(t.y, bB.x)));
+			}
+		}
+		double2 *dst = St + ((((size_t)zl * nb + b2) * qnum + q) * 3 + c) * ML * NP;
+#pragma unroll
+		for (int k = 0; k < SXS_TR_ROWS; k++) {
+			if (r0 + k < n) {
+				dst[(size_t)(mlrow0 + k) * NP + g0] = make_double2(re[k][0], im[k][0]);
+				if (has_g1) {
+					dst[(size_t)(mlrow0 + k) * NP + g1] = make_double2(re[k][1], im[k][1]);
+				}
+			}
+		}
+	}
+}
+
 /* ----------------------------------------------------- pose list handling */
 
 #define SXS_KEY_NONE 0xFFFFFFFFFFFFFFFFull
@@ -923,13 +1033,31 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		{
 			const int npair = (L + 2) / 2, rows = L + 2;
 			const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
-			int iters = (rows * N + 287) / 288;
-			int threads = 32 * ((rows * N + 32 * iters - 1) / (32 * iters));
-			if (threads > 288) threads = 288;
-			if (shm_t > 48 * 1024) {
-				SXS_CK(cudaFuncSetAttribute(k_translate_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+			const int GH = (N + 1) / 2;
+			int max_tiles = 0;
+			for (int ma = 0; ma < npair; ma++) {
+				const int mb = L - ma, nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
+				const int t = (nla + SXS_TR_ROWS - 1) / SXS_TR_ROWS + (nlb + SXS_TR_ROWS - 1) / SXS_TR_ROWS;
+				if (t > max_tiles) max_tiles = t;
 			}
-			k_translate_tiled<<<dim3(npair, 3 * Q, nb), threads, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+			const int threads_rt = 32 * ((max_tiles * GH + 31) / 32);
+			/* one output per thread: beyond L = 40 (the tiled form would need more than 512 threads), and for the
+			 * bit-identity test */
+			if (getenv("SXS_TRANSLATE_V1") != NULL || threads_rt > 512) {
+				int iters = (rows * N + 287) / 288;
+				int threads = 32 * ((rows * N + 32 * iters - 1) / (32 * iters));
+				if (threads > 288) threads = 288;
+				if (shm_t > 48 * 1024) {
+					SXS_CK(cudaFuncSetAttribute(k_translate_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+				}
+				k_translate_tiled<<<dim3(npair, 3 * Q, nb), threads, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+			} else {
+				/* 4-row x 2-column tiles: (ceil(nla/4) + ceil(nlb/4)) * GH threads, nla + nlb = L + 2 */
+				if (shm_t > 48 * 1024) {
+					SXS_CK(cudaFuncSetAttribute(k_translate_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+				}
+				k_translate_rt<<<dim3(npair, 3 * Q, nb), threads_rt, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+			}
 		}
 		SXS_CK_LAUNCH(); launches++;
 		timer_end(p, 1, st);

@@ -121,6 +121,46 @@ def test_properties_on_bench_workload():
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(base, tight))
 
 
+def test_translation_kernels_agree_bit_for_bit():
+    """K2c: the register-tiled translation (4 x 2 outputs per thread) writes the same St as the one-output-per-thread
+    form (SXS_TRANSLATE_V1) — scores, c1, c2 are equal to the last bit — at L = 15 and at L = 30 / Q = 100"""
+    def both(plan, idx):
+        os.environ.pop("SXS_TRANSLATE_V1", None)
+        new = plan.score(idx)
+        os.environ["SXS_TRANSLATE_V1"] = "1"
+        try:
+            old = plan.score(idx)
+        finally:
+            os.environ.pop("SXS_TRANSLATE_V1", None)
+        return new, old
+
+    G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+    R = np.load(os.path.join(GOLD, "golden_real70k.npz"))
+    plan = capi.Plan(int(G["L"]), G["qvals"])
+    plan.set_molecules(G["rec_coef"], G["lig_coef"])
+    plan.set_experiment(G["a"], G["scal"][1], G["scal"][2])
+    plan.set_translations(R["zvals"])
+    new, old = both(plan, R["index"][:20000])
+    plan.close()
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(new, old))
+    assert np.max(np.abs(new[0] / R["scores"][:20000] - 1)) < TOL
+
+    F = np.load(os.path.join(GOLD, "golden_l30.npz"))
+    L, q = int(F["L"]), F["qvals"]
+    A, _, _ = capi.expand(wl.MAP_PATH, F["rec_xyz"], names(F["rec_res"]), names(F["rec_atm"]), F["rec_radius"], q, L,
+                          sa=F["rec_sa"], water_mode=1)
+    B, _, _ = capi.expand(wl.MAP_PATH, F["lig_xyz"], names(F["lig_res"]), names(F["lig_atm"]), F["lig_radius"], q, L,
+                          sa=F["lig_sa"], water_mode=1)
+    plan = capi.Plan(L, q)
+    plan.set_molecules(A, B)
+    plan.set_experiment(F["a"], F["scal"][1], F["scal"][2])
+    plan.set_translations(F["zvals"])
+    new, old = both(plan, F["index"])
+    plan.close()
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(new, old))
+    assert np.max(np.abs(new[0] / F["scores"] - 1)) < TOL
+
+
 def test_dense_scan_topk():
     """every grid point of one z step (16 x 16 cells x 31^3 = 7.6 M points) is scored on the device and
     the best 64 come back; they are what the list API gives for the same indices, and no sampled point beats them"""
