@@ -667,12 +667,12 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
 /* [B200] 1.12 M points, (g1, g2, a2) order, 496-byte rows: 256x1 39.3 ms, 256x3 (80 regs, spills) 40.9, 128x4 38.4,
  * 128x5 45.1, 64x8 38.4, 512x1 41.1.  Band-major order + 512-byte rows: 128x4 36.1 (L1 data-pipe wavefronts per
  * 16-byte warp load 6.4 -> 4.2, the minimum: one per quarter warp); + next row requested before the MACs of the
- * current one: 128x4 35.7, 128x3 35.7, 64x6 35.4, 256x1 36.7. */
+ * current one: 128x4 35.7-36.5, 256x2 36.5, 512x1 38.1, 64x8 35.4 (launched), 32x16 35.2. */
 #ifndef SXS_CROSS_THREADS
-#define SXS_CROSS_THREADS 128
+#define SXS_CROSS_THREADS 64
 #endif
 #ifndef SXS_CROSS_MINBLOCKS
-#define SXS_CROSS_MINBLOCKS 4
+#define SXS_CROSS_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(SXS_CROSS_THREADS, SXS_CROSS_MINBLOCKS)
 k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0,
