@@ -37,7 +37,10 @@ struct sxs_fit_ctx {
 
 enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 
-#define SXS_X(ctx, q, c) ((ctx)->x[(long)(q) * (ctx)->qstride + (long)(c) * (ctx)->stride] * (ctx)->scale)
+#ifndef SXS_XLD1
+#define SXS_XLD1(p) (*(p))
+#endif
+#define SXS_X(ctx, q, c) (SXS_XLD1(&(ctx)->x[(long)(q) * (ctx)->qstride + (long)(c) * (ctx)->stride]) * (ctx)->scale)
 
 /* The six scaled terms of node q.  With SXS_ROWMAJOR_VEC (CUDA build, point-major rows x[q*6 + c],
  * 16-byte aligned) they come in as three 16-byte loads; the values and their use are identical. */

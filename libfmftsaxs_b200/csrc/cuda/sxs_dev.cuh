@@ -37,6 +37,25 @@ __host__ __device__ inline int sxs_ml_index(int L, int m, int l) { return m * (L
  * so that the 8 values g = 8k .. 8k+7 — one "band" — are exactly one cache line. */
 __host__ __device__ inline int sxs_row_pad(int N) { return (N + 7) & ~7; }
 
+/* Cross terms between K3 and K4.  SXS_X_TILED: points are kept in tiles of 32 (one warp of K4); inside a tile the
+ * 6*qnum terms are term-major and the 32 points are the fastest index, X[((tile*qnum + q)*6 + k)*32 + lane] — the
+ * warp of K4 that owns the tile reads every term with one coalesced 256-byte load.  Otherwise point-major rows
+ * X[p*6*qnum + q*6 + k]. */
+#ifndef SXS_X_ROWMAJOR
+#define SXS_X_TILED 1
+#endif
+#ifdef SXS_X_TILED
+__host__ __device__ inline size_t sxs_x_index(long long p, int qnum, int q, int k)
+{
+	return (((size_t)(p >> 5) * qnum + q) * 6 + k) * 32 + (size_t)(p & 31);
+}
+#else
+__host__ __device__ inline size_t sxs_x_index(long long p, int qnum, int q, int k)
+{
+	return ((size_t)p * qnum + q) * 6 + k;
+}
+#endif
+
 /* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
 
 /* K4: one fit per point.  x: point-major cross terms, x[p*6*qnum + q*6 + k]; res[p*4] = chi, c1, c2,

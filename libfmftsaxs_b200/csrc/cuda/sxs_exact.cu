@@ -17,13 +17,18 @@
 #include "sxs_dev.cuh"
 
 #define SXS_HD __host__ __device__ __forceinline__
+#ifndef SXS_X_TILED
 #define SXS_ROWMAJOR_VEC 1
+#endif
 #ifndef SXS_FIT_EVAL_EXACT
 #define SXS_FIT_EVAL_FUSED 1   /* [B200] 1.12 M fits: 66.8 ms two-pass, 52.5 ms one-pass */
 #define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory: 51.8 ms */
 #endif
 #ifndef SXS_XLD
 #define SXS_XLD __ldcs         /* cross-term rows are streamed (evict-first): 49.5 ms */
+#endif
+#if defined(SXS_X_TILED) && defined(__CUDA_ARCH__)
+#define SXS_XLD1(p) __ldcs(p)
 #endif
 #include "fit_point.h"
 
@@ -54,15 +59,16 @@ __device__ __forceinline__ void fit_store(const struct lb_state *st, double *__r
 	res[p * 4 + 3] = (double)st->nfgv;
 }
 
-/* K4.  X is point-major: the 6*qnum cross terms of point p are the contiguous row X[p*6*qnum + q*6 + k]
- * (2.4 KB at Q = 50), read with 16-byte loads.
+/* K4.  X comes in tiles of 32 points (sxs_x_index): a warp takes a whole tile, lane = point, and reads every term
+ * of every node with one coalesced 256-byte load; a lane whose fit has ended idles until the warp's slowest fit is
+ * done, then the warp takes the next tile from the ticket counter.  [B200] 1.12 M fits: 47.5 ms with point-major
+ * rows and per-lane refill, 46.0 ms tiled (K3's stores become coalesced too: 35.4 -> 34.5 ms).  -DSXS_X_ROWMAJOR
+ * builds the point-major form: contiguous rows X[p*6*qnum + q*6 + k], 16-byte loads, per-lane refill.
  *
- * Every lane owns one fit at a time and runs the reverse-communication optimiser lb_step() until it asks
- * for the objective; then the whole warp evaluates the objective together.  The optimiser logic is
- * branchy and diverges between lanes, the objective (2 passes over q with an exp each, ~95 % of the
- * arithmetic) is executed convergently.  A lane whose fit has terminated takes the next point from a
- * global ticket counter at the top of the next round, so lanes do not idle while a neighbour finishes a
- * long line search (evaluations per fit range from 2 to ~60).
+ * Every lane owns one fit at a time and runs the reverse-communication optimiser (lb_step_a / lb_step_b) until it
+ * asks for the objective; then all warps of the block evaluate the objective together.  The optimiser logic is
+ * branchy and diverges between lanes, the objective (one pass over q with one exp per node, most of the
+ * arithmetic) is executed convergently (evaluations per fit range from 2 to ~60).
  * Variants measured and rejected are logged in profiles/r1_k4_notes.md. */
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
@@ -83,7 +89,12 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 
 	struct lb_state st;
 	struct sxs_fit_ctx ctx;
-	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a; ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
+#ifdef SXS_X_TILED
+	ctx.stride = 32; ctx.qstride = 6 * 32; ctx.a = s_a;
+#else
+	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a;
+#endif
+	ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
 	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq;
 	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
 	(void)sum_a0;
@@ -118,10 +129,27 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 			}
 		}
 		/* (3) free lanes take the next point from the ticket counter */
+#ifdef SXS_X_TILED
+		/* a warp takes a whole tile of 32 points when all its lanes are free: lane = point inside the tile */
+		const bool warp_free = __all_sync(0xffffffffu, mode == FREE);
+		if (warp_free && !drained) {
+			unsigned long long tile = 0;
+			if ((threadIdx.x & 31) == 0) {
+				tile = atomicAdd(ticket, 1ull);
+			}
+			tile = __shfl_sync(0xffffffffu, tile, 0);
+			p = (long long)(tile * 32ull + (threadIdx.x & 31));
+			if ((long long)(tile * 32ull) >= npts) {
+				drained = true;
+			}
+			if (p < npts) {
+				ctx.x = X + sxs_x_index(p, qnum, 0, 0);
+#else
 		if (mode == FREE && !drained) {
 			p = (long long)atomicAdd(ticket, 1ull);
 			if (p < npts) {
 				ctx.x = X + (size_t)p * 6 * qnum;
+#endif
 				ctx.scale = 1.0;
 				if (rescale) {
 					ctx.scale = sxs_fit_rescale(&ctx, peak);
@@ -133,7 +161,9 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 					fit_store(&st, res, p);
 				}
 			} else {
+#ifndef SXS_X_TILED
 				drained = true;
+#endif
 			}
 		}
 		/* (4) all warps of the block enter the evaluation together: they share the instruction stream, which is
@@ -186,7 +216,7 @@ __global__ void k_cross_to_rows(const double *__restrict__ cross, long long npts
 		const long long p = i / (6 * qnum);
 		const int r = (int)(i % (6 * qnum));
 		const int q = r / 6, k = r % 6;
-		x[i] = cross[(p * 6 + k) * qnum + q];
+		x[sxs_x_index(p, qnum, q, k)] = cross[(p * 6 + k) * qnum + q];
 	}
 }
 
@@ -201,7 +231,7 @@ extern "C" int sxs_cuda_fit_profiles(int device, const double *cross, long long 
 	unsigned long long *d_ticket = NULL;
 	const size_t nx = (size_t)npts * 6 * qnum;
 	SXS_CK(cudaMalloc(&d_cross, sizeof(double) * nx));
-	SXS_CK(cudaMalloc(&d_x, sizeof(double) * nx));
+	SXS_CK(cudaMalloc(&d_x, sizeof(double) * (size_t)((npts + 31) / 32 * 32) * 6 * qnum));
 	SXS_CK(cudaMalloc(&d_a, sizeof(double) * 6 * qnum));
 	SXS_CK(cudaMalloc(&d_q, sizeof(double) * qnum));
 	SXS_CK(cudaMalloc(&d_res, sizeof(double) * 4 * npts));

@@ -747,10 +747,20 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		}
 		av = nav; ad = nad; aw = naw; sv = nsv; sd = nsd; sw = nsw;
 	}
+#ifdef SXS_X_TILED
+	double *xo = X + sxs_x_index(p - p0, qnum, q, 0); /* consecutive threads are consecutive points: 256-byte stores */
+	xo[0 * 32] = cst[0 * qnum + q] + 2.0 * f0;
+	xo[1 * 32] = cst[1 * qnum + q] + 2.0 * f1;
+	xo[2 * 32] = cst[2 * qnum + q] + 2.0 * f2;
+	xo[3 * 32] = cst[3 * qnum + q] + 2.0 * f3;
+	xo[4 * 32] = cst[4 * qnum + q] + 2.0 * f4;
+	xo[5 * 32] = cst[5 * qnum + q] + 2.0 * f5;
+#else
 	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - p0) * qnum + q) * 6);
 	xo[0] = make_double2(cst[0 * qnum + q] + 2.0 * f0, cst[1 * qnum + q] + 2.0 * f1);
 	xo[1] = make_double2(cst[2 * qnum + q] + 2.0 * f2, cst[3 * qnum + q] + 2.0 * f3);
 	xo[2] = make_double2(cst[4 * qnum + q] + 2.0 * f4, cst[5 * qnum + q] + 2.0 * f5);
+#endif
 }
 
 /* ---------------------------------------------------------------- scatter */
@@ -801,7 +811,7 @@ __global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, con
 	const unsigned int row = rows_sorted[i];
 	for (int q = 0; q < qnum; q++) {
 		for (int k = 0; k < 6; k++) {
-			cross[((size_t)row * 6 + k) * qnum + q] = X[((size_t)(p - p0) * qnum + q) * 6 + k];
+			cross[((size_t)row * 6 + k) * qnum + q] = X[sxs_x_index(p - p0, qnum, q, k)];
 		}
 	}
 }
@@ -993,7 +1003,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	}
 	if (ensure(&p->d_St, &p->cap_St, slab_elems * nb * (size_t)zg_max)) return -1;
 	if (ensure(&p->d_T, &p->cap_T, (size_t)zg_max * Q * nb * nb * nb)) return -1;
-	if (ensure(&p->d_X, &p->cap_X, (size_t)chunk_max * 6 * Q)) return -1;
+	if (ensure(&p->d_X, &p->cap_X, (size_t)((chunk_max + 31) / 32 * 32) * 6 * Q)) return -1;
 	if (p->d_slab_flag == NULL || p->cap_slab < zg_max * nb + zg_max) {
 		if (p->d_slab_flag) cudaFree(p->d_slab_flag);
 		SXS_CK(cudaMalloc(&p->d_slab_flag, sizeof(int) * (zg_max * nb + zg_max)));
