@@ -675,7 +675,7 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
 #define SXS_CROSS_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(SXS_CROSS_THREADS, SXS_CROSS_MINBLOCKS)
-k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, int z0,
+k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, long long xbase, int z0,
         const double2 *__restrict__ At, const double2 *__restrict__ St, const double2 *__restrict__ tw,
         const double *__restrict__ cst, double *__restrict__ X)
 {
@@ -748,7 +748,7 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		av = nav; ad = nad; aw = naw; sv = nsv; sd = nsd; sw = nsw;
 	}
 #ifdef SXS_X_TILED
-	double *xo = X + sxs_x_index(p - p0, qnum, q, 0); /* consecutive threads are consecutive points: 256-byte stores */
+	double *xo = X + sxs_x_index(p - xbase, qnum, q, 0); /* consecutive threads are consecutive points: 256-byte stores */
 	xo[0 * 32] = cst[0 * qnum + q] + 2.0 * f0;
 	xo[1 * 32] = cst[1 * qnum + q] + 2.0 * f1;
 	xo[2 * 32] = cst[2 * qnum + q] + 2.0 * f2;
@@ -756,7 +756,7 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 	xo[4 * 32] = cst[4 * qnum + q] + 2.0 * f4;
 	xo[5 * 32] = cst[5 * qnum + q] + 2.0 * f5;
 #else
-	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - p0) * qnum + q) * 6);
+	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - xbase) * qnum + q) * 6);
 	xo[0] = make_double2(cst[0 * qnum + q] + 2.0 * f0, cst[1 * qnum + q] + 2.0 * f1);
 	xo[1] = make_double2(cst[2 * qnum + q] + 2.0 * f2, cst[3 * qnum + q] + 2.0 * f3);
 	xo[2] = make_double2(cst[4 * qnum + q] + 2.0 * f4, cst[5 * qnum + q] + 2.0 * f5);
@@ -797,8 +797,8 @@ __global__ void k_gather_sorted(const unsigned int *__restrict__ pid_incl, long 
 
 /* cross terms of sorted rows back to list order (stage access for the parity tests) */
 __global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, const unsigned int *__restrict__ pid_incl,
-                               long long nvalid, long long p0, long long p1, const double *__restrict__ X,
-                               int qnum, double *__restrict__ cross)
+                               long long nvalid, long long p0, long long p1, long long xbase,
+                               const double *__restrict__ X, int qnum, double *__restrict__ cross)
 {
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= nvalid) {
@@ -811,7 +811,7 @@ __global__ void k_gather_cross(const unsigned int *__restrict__ rows_sorted, con
 	const unsigned int row = rows_sorted[i];
 	for (int q = 0; q < qnum; q++) {
 		for (int k = 0; k < 6; k++) {
-			cross[((size_t)row * 6 + k) * qnum + q] = X[sxs_x_index(p - p0, qnum, q, k)];
+			cross[((size_t)row * 6 + k) * qnum + q] = X[sxs_x_index(p - xbase, qnum, q, k)];
 		}
 	}
 }
@@ -1013,6 +1013,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	int *h_zlist = (int *)malloc(sizeof(int) * zg_max);
 
 	long long nslabs_total = 0, ngroups = 0;
+	long long xbase = -1, xend = -1; /* points [xbase, xend) have their cross terms in X and are not fitted yet */
 	int z = z_lo;
 	while (z < z_hi) {
 		/* gather up to zg_max z steps that hold points; they need not be contiguous, only ordered */
@@ -1073,28 +1074,51 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		timer_end(p, 1, st);
 		nslabs_total += (long long)zspan * nb;
 
-		for (long long c0 = g0; c0 < g1; c0 += chunk_max) {
-			const long long c1e = (c0 + chunk_max < g1) ? c0 + chunk_max : g1;
+		/* Cross terms of consecutive z groups pile up in X (point p at X index p - xbase) and are fitted by ONE launch
+		 * when X is full or the list ends: a sparse list at large L has many z groups of a few thousand points each,
+		 * far fewer than the ~113 000 fits K4 keeps in flight. */
+		for (long long c0 = g0; c0 < g1;) {
+			if (xbase < 0) {
+				xbase = c0;
+			}
+			if (c0 - xbase >= chunk_max) { /* X is full: fit what it holds */
+				timer_begin(p, 3, st);
+				if (sxs_launch_fit(p->d_X, c0 - xbase, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)xbase * 4,
+				                   p->d_ticket, st) != 0) {
+					free(h_zlist);
+					return -1;
+				}
+				launches++;
+				timer_end(p, 3, st);
+				xbase = c0;
+			}
+			const long long room = xbase + chunk_max;
+			const long long c1e = (room < g1) ? room : g1;
 			const long long cnt = c1e - c0;
 			dim3 grid((unsigned)((cnt + SXS_CROSS_THREADS - 1) / SXS_CROSS_THREADS), Q);
 			timer_begin(p, 2, st);
-			k_cross<<<grid, SXS_CROSS_THREADS, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, z_first, p->d_At, p->d_St, p->d_tw,
-			                                                 p->d_const, p->d_X);
+			k_cross<<<grid, SXS_CROSS_THREADS, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, xbase, z_first, p->d_At, p->d_St,
+			                                                 p->d_tw, p->d_const, p->d_X);
 			SXS_CK_LAUNCH(); launches++;
 			timer_end(p, 2, st);
 			if (d_cross_out != NULL) {
-				k_gather_cross<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_rows_sorted, p->d_pid, nvalid, c0, c1e,
+				k_gather_cross<<<(unsigned)((nvalid + 255) / 256), 256, 0, st>>>(p->d_rows_sorted, p->d_pid, nvalid, c0, c1e, xbase,
 				                                                              p->d_X, Q, d_cross_out);
 				SXS_CK_LAUNCH(); launches++;
 			}
-			timer_begin(p, 3, st);
-			if (sxs_launch_fit(p->d_X, cnt, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)c0 * 4, p->d_ticket, st) != 0) {
-				free(h_zlist);
-				return -1;
-			}
-			launches++;
-			timer_end(p, 3, st);
+			xend = c1e;
+			c0 = c1e;
 		}
+	}
+	if (xbase >= 0 && xend > xbase) {
+		timer_begin(p, 3, st);
+		if (sxs_launch_fit(p->d_X, xend - xbase, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res + (size_t)xbase * 4,
+		                   p->d_ticket, st) != 0) {
+			free(h_zlist);
+			return -1;
+		}
+		launches++;
+		timer_end(p, 3, st);
 	}
 	free(h_zlist);
 

@@ -12,6 +12,6 @@ tail -c 600 $out/bench_$tag.json
 tail -c 400 $out/bench_ref_$tag.json; tail -4 $out/bench_ref_$tag.err
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv \
     --log-file $out/launches_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_launches_$tag.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name regex:"k_fit|k_cross|k_translate_tiled" --launch-skip 9 --launch-count 3 \
+ncu --set full --clock-control none --import-source on --kernel-name regex:"k_fit|k_cross|k_translate_rt" --launch-skip 9 --launch-count 3 \
     -o $out/prof_${tag}_k34 -f python bench.py --steps 1 --warmup 3 --nrot 70000 --nz 16 --no-cpu-baseline > $out/ncu_full_$tag.log 2>&1
 tail -2 $out/ncu_full_$tag.log
