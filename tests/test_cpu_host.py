@@ -385,11 +385,11 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/tools"), reason="reference tree not present")
 def test_reference_tools_compile_unmodified_against_our_headers(tmp_path):
-    """drop-in at source level: the reference's own correlate.c / single_saxs.c build against include/ and link
-    against libfmftsaxs.so without edits"""
-    for tool in ("correlate", "single_saxs"):
+    """drop-in at source level: the reference's own correlate.c / single_saxs.c / score_ft_naive.c build against
+    include/ and link against libfmftsaxs.so without edits"""
+    for tool in ("correlate", "single_saxs", "score_ft_naive"):
         out = tmp_path / tool
-        r = subprocess.run(["gcc", "-std=c11", "-O1", "-w", "-I" + os.path.join(REPO, "include", "fmftsaxs"),
+        r = subprocess.run(["gcc", "-std=c11", "-O1", "-w", "-D_GNU_SOURCE", "-I" + os.path.join(REPO, "include", "fmftsaxs"),
                             "-I" + os.path.join(REPO, "include"), "/root/reference/tools/%s.c" % tool,
                             "-L" + os.path.join(REPO, "libfmftsaxs_b200"), "-lfmftsaxs", "-lm", "-o", str(out)],
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

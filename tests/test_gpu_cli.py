@@ -121,3 +121,30 @@ def test_score_ft_naive_cli_matches_reference_tool_and_the_fft_path(files):
           np.abs(dev[:, 1]).max(), np.abs(dev[:, 2]).max()))
     # different hydration weights (joined vs separate molecules) and different truncations: same physics, not same digits
     assert np.abs(dev[:, 0]).max() < 0.25
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "dropin_correlate")), reason="drop-in tools not built (need /root/reference at build time)")
+def test_reference_tool_sources_run_on_the_product_library(files):
+    """Drop-in proof: the reference's OWN tools/correlate.c and tools/single_saxs.c, compiled unmodified against include/
+    and linked to libfmftsaxs.so (oracle/Makefile `dropin`), give the rows of the all-reference build"""
+    d = files
+    common = [MAP, PRM, str(d / "ft.000"), str(d / "rot.prm"), str(d / "rec.pdb"), str(d / "lig.pdb"), str(d / "exp.dat"), "15"]
+    r = subprocess.run([os.path.join(REF, "dropin_correlate")] + common + [str(d / "eul_drop"), str(d / "out_drop")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    if not os.path.exists(d / "out_ref"):
+        subprocess.run([os.path.join(REF, "ref_correlate")] + common + [str(d / "eul_ref"), str(d / "out_ref")], check=True,
+                       stdout=subprocess.DEVNULL, timeout=900)
+    assert open(d / "eul_drop").read() == open(d / "eul_ref").read()
+    drop = [l.split("\t") for l in open(d / "out_drop").read().splitlines()]
+    ref = [l.split("\t") for l in open(d / "out_ref").read().splitlines()]
+    assert len(drop) == len(ref) > 0
+    for a, b in zip(drop, ref):
+        assert a[0].strip() == b[0].strip() and a[1] == b[1]
+        for x, y in zip(a[2:], b[2:]):
+            assert abs(float(x) - float(y)) <= 1.001e-3
+    s_common = [MAP, PRM, str(d / "rec.pdb"), str(d / "lig.pdb"), "1.0", "0.0", "15"]
+    subprocess.run([os.path.join(REF, "dropin_single_saxs")] + s_common + [str(d / "p_drop")], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([os.path.join(REF, "ref_single_saxs")] + s_common + [str(d / "p_ref2")], check=True, stdout=subprocess.DEVNULL)
+    a, b = np.loadtxt(d / "p_drop"), np.loadtxt(d / "p_ref2")
+    assert a.shape == b.shape == (50, 3) and np.max(np.abs(a[:, 1] / b[:, 1] - 1)) < 1e-6
