@@ -79,7 +79,8 @@ int sxs_cuda_plan_score_dev_i64(sxs_cuda_plan *plan, const long long *d_index, l
                                 double *d_scores, double *d_c1, double *d_c2, void *stream);
 
 /* Counters of the last score call: [0] distinct grid points fitted, [1] (z,beta2) slabs translated,
- * [2] kernel launches, [3] objective evaluations summed over fits, [4] z groups. */
+ * [2] kernel launches, [3] K3 threads that took more than one point (points differing only in a2 share a thread;
+ * 0 = one point per thread), [4] z groups. */
 int sxs_cuda_plan_stats(const sxs_cuda_plan *plan, long long *stats5);
 
 /* Histogram of objective evaluations per fit over the distinct points of the last score call

@@ -361,4 +361,4 @@ class Plan:
     def stats(self):
         st = (C.c_longlong * 5)()
         lib().sxs_cuda_plan_stats(self._h, st)
-        return dict(points=st[0], slabs=st[1], launches=st[2], evaluations=st[3], groups=st[4])
+        return dict(points=st[0], slabs=st[1], launches=st[2], cross_groups=st[3], groups=st[4])

@@ -674,8 +674,16 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
 #ifndef SXS_CROSS_MINBLOCKS
 #define SXS_CROSS_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(SXS_CROSS_THREADS, SXS_CROSS_MINBLOCKS)
+/* K > 1: points that differ only in a2 (same cell, g1, g2) share every operand and all nine inner sums; they differ
+ * in the phase w^(m a2) applied once per m.  A thread then takes up to K such points (consecutive in key order; the
+ * groups are formed per launch by k_group_*): one set of loads and MACs, K phase accumulations.  Each point still sees
+ * exactly the operations of the K = 1 form in the same order, so X is bit-identical.  groups[i] = first point of the
+ * group (relative to p0) | (members - 1) << SXS_GROUP_SHIFT. */
+#define SXS_GROUP_SHIFT 28
+template <int K>
+__global__ void __launch_bounds__(SXS_CROSS_THREADS, (K == 1) ? SXS_CROSS_MINBLOCKS : (K == 2 ? 6 : 4))
 k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long p0, long long p1, long long xbase, int z0,
+        const unsigned int *__restrict__ groups, unsigned int ngroups,
         const double2 *__restrict__ At, const double2 *__restrict__ St, const double2 *__restrict__ tw,
         const double *__restrict__ cst, double *__restrict__ X)
 {
@@ -685,14 +693,27 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		s_tw[i] = tw[i];
 	}
 	__syncthreads();
-	const long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= p1) {
-		return;
+	long long p;
+	int members = 1;
+	if (K == 1) {
+		p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+		if (p >= p1) {
+			return;
+		}
+	} else {
+		const unsigned int gi = blockIdx.x * blockDim.x + threadIdx.x;
+		if (gi >= ngroups) {
+			return;
+		}
+		const unsigned int word = groups[gi];
+		p = p0 + (long long)(word & ((1u << SXS_GROUP_SHIFT) - 1u));
+		members = (int)(word >> SXS_GROUP_SHIFT) + 1;
 	}
 	const int q = blockIdx.y;
 	const int NP = sxs_row_pad(N), nband = NP / 8;
 	unsigned long long key = pkeys[p];
-	const int a2 = (int)(key % N); key /= N;
+	int a2[K];
+	a2[0] = (int)(key % N); key /= N;
 	int g2 = (int)(key % 8); key /= 8;
 	const int g1 = (int)(key % N); key /= N;
 	g2 += 8 * (int)(key % nband); key /= nband;
@@ -700,13 +721,25 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 	const int b2 = (int)(key % nb);
 	const int z = (int)(key / nb);
 	const int slab = (z - z0) * nb + b2;
+#pragma unroll
+	for (int k = 1; k < K; k++) {
+		a2[k] = (k < members) ? (int)(pkeys[p + k] % N) : 0;
+	}
 
 	const size_t cstride = (size_t)ML * NP;
 	const double2 *a_ptr = At + (((size_t)b1 * qnum + q) * 3) * cstride + g1;
 	const double2 *s_ptr = St + (((size_t)slab * qnum + q) * 3) * cstride + g2;
 
-	double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0;
-	int ka = 0; /* (m*a2) mod N */
+	double f[K][6];
+	int ka[K]; /* (m*a2) mod N */
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		ka[k] = 0;
+#pragma unroll
+		for (int j = 0; j < 6; j++) {
+			f[k][j] = 0.0;
+		}
+	}
 	/* one flat loop over the ML (m, l) rows; the six operands of the next row are requested before the nine complex
 	 * MACs of the current one, so that a warp always has a row in flight behind its arithmetic */
 	double2 cvv = {0, 0}, cvd = {0, 0}, cvw = {0, 0}, cdd = {0, 0}, cdw = {0, 0}, cww = {0, 0};
@@ -727,19 +760,22 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		cmac(cdw, ad, sw); cmac(cdw, aw, sd);
 		cmac(cww, aw, sw);
 		if (l == L) {
-			const double2 w = s_tw[ka];
 			const double fac = (m == 0) ? 1.0 : 2.0;
-			f0 += fac * (w.x * cvv.x - w.y * cvv.y);
-			f1 += fac * (w.x * cvd.x - w.y * cvd.y);
-			f2 += fac * (w.x * cvw.x - w.y * cvw.y);
-			f3 += fac * (w.x * cdd.x - w.y * cdd.y);
-			f4 += fac * (w.x * cdw.x - w.y * cdw.y);
-			f5 += fac * (w.x * cww.x - w.y * cww.y);
-			cvv = cvd = cvw = cdd = cdw = cww = make_double2(0.0, 0.0);
-			ka += a2;
-			if (ka >= N) {
-				ka -= N;
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				const double2 w = s_tw[ka[k]];
+				f[k][0] += fac * (w.x * cvv.x - w.y * cvv.y);
+				f[k][1] += fac * (w.x * cvd.x - w.y * cvd.y);
+				f[k][2] += fac * (w.x * cvw.x - w.y * cvw.y);
+				f[k][3] += fac * (w.x * cdd.x - w.y * cdd.y);
+				f[k][4] += fac * (w.x * cdw.x - w.y * cdw.y);
+				f[k][5] += fac * (w.x * cww.x - w.y * cww.y);
+				ka[k] += a2[k];
+				if (ka[k] >= N) {
+					ka[k] -= N;
+				}
 			}
+			cvv = cvd = cvw = cdd = cdw = cww = make_double2(0.0, 0.0);
 			m++;
 			l = m;
 		} else {
@@ -747,21 +783,78 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 		}
 		av = nav; ad = nad; aw = naw; sv = nsv; sd = nsd; sw = nsw;
 	}
+	const double c0 = cst[0 * qnum + q], c1 = cst[1 * qnum + q], c2 = cst[2 * qnum + q], c3 = cst[3 * qnum + q],
+	             c4 = cst[4 * qnum + q], c5 = cst[5 * qnum + q];
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+		if (k < members) {
 #ifdef SXS_X_TILED
-	double *xo = X + sxs_x_index(p - xbase, qnum, q, 0); /* consecutive threads are consecutive points: 256-byte stores */
-	xo[0 * 32] = cst[0 * qnum + q] + 2.0 * f0;
-	xo[1 * 32] = cst[1 * qnum + q] + 2.0 * f1;
-	xo[2 * 32] = cst[2 * qnum + q] + 2.0 * f2;
-	xo[3 * 32] = cst[3 * qnum + q] + 2.0 * f3;
-	xo[4 * 32] = cst[4 * qnum + q] + 2.0 * f4;
-	xo[5 * 32] = cst[5 * qnum + q] + 2.0 * f5;
+			double *xo = X + sxs_x_index(p + k - xbase, qnum, q, 0); /* consecutive points: 256-byte stores per warp */
+			xo[0 * 32] = c0 + 2.0 * f[k][0];
+			xo[1 * 32] = c1 + 2.0 * f[k][1];
+			xo[2 * 32] = c2 + 2.0 * f[k][2];
+			xo[3 * 32] = c3 + 2.0 * f[k][3];
+			xo[4 * 32] = c4 + 2.0 * f[k][4];
+			xo[5 * 32] = c5 + 2.0 * f[k][5];
 #else
-	double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p - xbase) * qnum + q) * 6);
-	xo[0] = make_double2(cst[0 * qnum + q] + 2.0 * f0, cst[1 * qnum + q] + 2.0 * f1);
-	xo[1] = make_double2(cst[2 * qnum + q] + 2.0 * f2, cst[3 * qnum + q] + 2.0 * f3);
-	xo[2] = make_double2(cst[4 * qnum + q] + 2.0 * f4, cst[5 * qnum + q] + 2.0 * f5);
+			double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p + k - xbase) * qnum + q) * 6);
+			xo[0] = make_double2(c0 + 2.0 * f[k][0], c1 + 2.0 * f[k][1]);
+			xo[1] = make_double2(c2 + 2.0 * f[k][2], c3 + 2.0 * f[k][3]);
+			xo[2] = make_double2(c4 + 2.0 * f[k][4], c5 + 2.0 * f[k][5]);
 #endif
+		}
+	}
 }
+
+/* start[i] = i where point p0+i opens a run of points that differ only in a2, else 0; a running maximum then gives
+ * every point the start of its run */
+__global__ void k_group_heads(const unsigned long long *__restrict__ pkeys, long long p0, unsigned int cnt,
+                              unsigned long long per_run, unsigned int *__restrict__ start)
+{
+	const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnt) {
+		return;
+	}
+	const bool head = (i == 0) || (pkeys[p0 + i] / per_run != pkeys[p0 + i - 1] / per_run);
+	start[i] = head ? i : 0u;
+}
+
+/* lead[i] = 1 where point i opens a group of K inside its run */
+__global__ void k_group_leads(const unsigned int *__restrict__ run_start, unsigned int cnt, int K,
+                              unsigned int *__restrict__ lead)
+{
+	const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnt) {
+		return;
+	}
+	lead[i] = ((i - run_start[i]) % (unsigned)K == 0u) ? 1u : 0u;
+}
+
+/* lead_excl = exclusive sum of lead = group number of every leading point; groups[cnt] receives the number of groups */
+__global__ void k_group_emit(const unsigned int *__restrict__ run_start, const unsigned int *__restrict__ lead_excl,
+                             unsigned int cnt, int K, unsigned int *__restrict__ groups)
+{
+	const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= cnt) {
+		return;
+	}
+	const unsigned int rs = run_start[i];
+	const bool lead = (i - rs) % (unsigned)K == 0u;
+	if (lead) {
+		unsigned int members = 1;
+		while (members < (unsigned)K && i + members < cnt && run_start[i + members] == rs) {
+			members++;
+		}
+		groups[lead_excl[i]] = i | ((members - 1u) << SXS_GROUP_SHIFT);
+	}
+	if (i == cnt - 1) {
+		groups[cnt] = lead_excl[i] + (lead ? 1u : 0u);
+	}
+}
+
+struct sxs_max_op {
+	__device__ __forceinline__ unsigned int operator()(unsigned int a, unsigned int b) const { return a > b ? a : b; }
+};
 
 /* ---------------------------------------------------------------- scatter */
 
@@ -914,7 +1007,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		p->d_keys = p->d_keys_sorted = p->d_pkeys = NULL;
 		p->d_rows = p->d_rows_sorted = p->d_pid = NULL;
 		if (ensure(&p->d_keys, &c1_, (size_t)nout) || ensure(&p->d_keys_sorted, &c2_, (size_t)nout) ||
-		    ensure(&p->d_pkeys, &c3_, (size_t)nout) || ensure(&p->d_rows, &c4_, (size_t)nout) ||
+		    ensure(&p->d_pkeys, &c3_, (size_t)nout) || ensure(&p->d_rows, &c4_, (size_t)nout + 1) ||
 		    ensure(&p->d_rows_sorted, &c5_, (size_t)nout) || ensure(&p->d_pid, &c6_, (size_t)nout)) {
 			p->cap_rows = 0;
 			return -1;
@@ -1014,6 +1107,24 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 
 	long long nslabs_total = 0, ngroups = 0;
 	long long xbase = -1, xend = -1; /* points [xbase, xend) have their cross terms in X and are not fitted yet */
+	/* K3 threads take up to K points that differ only in a2: SXS_CROSS_GROUP = 1 (never), 2, 4; unset = by run length */
+	int cross_group = 0;
+	if (getenv("SXS_CROSS_GROUP") != NULL) {
+		cross_group = atoi(getenv("SXS_CROSS_GROUP"));
+		if (cross_group != 1 && cross_group != 2 && cross_group != 4) cross_group = 0;
+	}
+	if (cross_group != 1) {
+		size_t n1 = 0, n2 = 0;
+		cub::DeviceScan::InclusiveScan(NULL, n1, (unsigned int *)NULL, (unsigned int *)NULL, sxs_max_op(), (int)chunk_max, st);
+		cub::DeviceScan::ExclusiveSum(NULL, n2, (unsigned int *)NULL, (unsigned int *)NULL, (int)chunk_max, st);
+		if (n2 > n1) n1 = n2;
+		if (n1 + 256 > p->cap_cub) {
+			unsigned char *tmp = (unsigned char *)p->d_cub;
+			size_t c = p->cap_cub;
+			if (ensure(&tmp, &c, n1 + 256)) { free(h_zlist); return -1; }
+			p->d_cub = tmp; p->cap_cub = c;
+		}
+	}
 	int z = z_lo;
 	while (z < z_hi) {
 		/* gather up to zg_max z steps that hold points; they need not be contiguous, only ordered */
@@ -1095,10 +1206,54 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 			const long long room = xbase + chunk_max;
 			const long long c1e = (room < g1) ? room : g1;
 			const long long cnt = c1e - c0;
-			dim3 grid((unsigned)((cnt + SXS_CROSS_THREADS - 1) / SXS_CROSS_THREADS), Q);
 			timer_begin(p, 2, st);
-			k_cross<<<grid, SXS_CROSS_THREADS, sizeof(double2) * N, st>>>(L, Q, p->d_pkeys, c0, c1e, xbase, z_first, p->d_At, p->d_St,
-			                                                 p->d_tw, p->d_const, p->d_X);
+			/* points that differ only in a2 share all operands: count the runs, then let a thread take up to K points
+			 * of a run (d_keys and d_rows are free once the points are compacted) */
+			int K = 1;
+			unsigned int ngroups_k = 0;
+			if (cross_group != 1 && cnt < (1ll << SXS_GROUP_SHIFT) && cnt >= 2) {
+				unsigned int *run_start = (unsigned int *)p->d_keys, *lead = run_start + nout, *groups = p->d_rows;
+				const unsigned gc = (unsigned)((cnt + 255) / 256);
+				k_group_heads<<<gc, 256, 0, st>>>(p->d_pkeys, c0, (unsigned)cnt, (unsigned long long)N, run_start);
+				SXS_CK_LAUNCH(); launches++;
+				size_t tb2 = p->cap_cub;
+				SXS_CK(cub::DeviceScan::InclusiveScan(p->d_cub, tb2, run_start, run_start, sxs_max_op(), (int)cnt, st));
+				for (int pass = 0; pass < 2; pass++) {
+					const int kk = (pass == 0) ? (1 << 30) : K; /* pass 0 counts the runs */
+					k_group_leads<<<gc, 256, 0, st>>>(run_start, (unsigned)cnt, kk, lead);
+					SXS_CK_LAUNCH(); launches++;
+					tb2 = p->cap_cub;
+					SXS_CK(cub::DeviceScan::ExclusiveSum(p->d_cub, tb2, lead, lead, (int)cnt, st));
+					k_group_emit<<<gc, 256, 0, st>>>(run_start, lead, (unsigned)cnt, kk, groups);
+					SXS_CK_LAUNCH(); launches += 2;
+					SXS_CK(cudaMemcpyAsync(&ngroups_k, groups + cnt, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+					SXS_CK(cudaStreamSynchronize(st));
+					if (pass == 0) {
+						const double per_run = (double)cnt / (double)(ngroups_k > 0 ? ngroups_k : 1);
+						K = (cross_group > 1) ? cross_group : (per_run < 1.04 ? 1 : (per_run < 1.8 ? 2 : 4));
+						if (K == 1) {
+							break;
+						}
+					}
+				}
+			}
+			const size_t shm_c = sizeof(double2) * N;
+			if (K == 1) {
+				dim3 grid((unsigned)((cnt + SXS_CROSS_THREADS - 1) / SXS_CROSS_THREADS), Q);
+				k_cross<1><<<grid, SXS_CROSS_THREADS, shm_c, st>>>(L, Q, p->d_pkeys, c0, c1e, xbase, z_first, NULL, 0u, p->d_At, p->d_St,
+				                                        p->d_tw, p->d_const, p->d_X);
+			} else {
+				dim3 grid((ngroups_k + SXS_CROSS_THREADS - 1) / SXS_CROSS_THREADS, Q);
+				if (K == 2) {
+					k_cross<2><<<grid, SXS_CROSS_THREADS, shm_c, st>>>(L, Q, p->d_pkeys, c0, c1e, xbase, z_first, p->d_rows, ngroups_k,
+					                                        p->d_At, p->d_St, p->d_tw, p->d_const, p->d_X);
+				} else {
+					K = 4;
+					k_cross<4><<<grid, SXS_CROSS_THREADS, shm_c, st>>>(L, Q, p->d_pkeys, c0, c1e, xbase, z_first, p->d_rows, ngroups_k,
+					                                        p->d_At, p->d_St, p->d_tw, p->d_const, p->d_X);
+				}
+				p->stats[3] += ngroups_k;
+			}
 			SXS_CK_LAUNCH(); launches++;
 			timer_end(p, 2, st);
 			if (d_cross_out != NULL) {

@@ -161,6 +161,76 @@ def test_translation_kernels_agree_bit_for_bit():
     assert np.max(np.abs(new[0] / F["scores"] - 1)) < TOL
 
 
+def test_grouped_cross_kernel_is_bit_identical():
+    """K3 threads that take 2 or 4 points differing only in a2 (same cell, g1, g2: shared operands and inner sums) write
+    the same cross terms as one point per thread: scores, c1, c2 equal bit for bit on a dense list, on a sparse one and
+    across chunk boundaries; unset, the run length decides"""
+    def run(plan, idx, group):
+        old = os.environ.get("SXS_CROSS_GROUP")
+        if group is None:
+            os.environ.pop("SXS_CROSS_GROUP", None)
+        else:
+            os.environ["SXS_CROSS_GROUP"] = str(group)
+        try:
+            return plan.score(idx), plan.stats()
+        finally:
+            if old is None:
+                os.environ.pop("SXS_CROSS_GROUP", None)
+            else:
+                os.environ["SXS_CROSS_GROUP"] = old
+
+    w = wl.make("cfg3_3k+1.5k_L15_Q50_70kx64z", nrot=20000, nz=3)
+    q, L = w["qvals"], w["L"]
+    nb, N = L + 1, 2 * L + 1
+    A, _, _ = capi.expand(wl.MAP_PATH, w["rec"]["xyz"], w["rec"]["res"], w["rec"]["atm"], w["rec"]["radius"], q, L,
+                          sa=w["rec"]["sa"], water_mode=1)
+    B, _, _ = capi.expand(wl.MAP_PATH, w["lig"]["xyz"], w["lig"]["res"], w["lig"]["atm"], w["lig"]["radius"], q, L,
+                          sa=w["lig"]["sa"], water_mode=1)
+    eq, ei, ee = wl.experimental_curve(A, B, q)
+    a, scal = capi.opt_params(eq, ei, ee, q, wl.mean_radius(w["rec"], w["lig"]))
+    idx = w["index"].astype(np.int64)
+    # fold the (beta1, beta2) digits onto 3 x 2 values: cells of ~3300 rows, ~3.5 rows per (g1, g2) pair
+    n3 = N ** 3
+    ang, cell = idx % n3, idx // n3
+    b2, b1, z = cell % nb, (cell // nb) % nb, cell // (nb * nb)
+    dense = (((z * nb + (b1 % 3) + 5) * nb + (b2 % 2) + 7) * n3 + ang).astype(np.int32)
+    plan = capi.Plan(L, q)
+    plan.set_molecules(A, B)
+    plan.set_experiment(a, scal[1], scal[2])
+    plan.set_translations(w["zvals"])
+    for lst in (dense, w["index"]):
+        base, st1 = run(plan, lst, 1)
+        assert st1["cross_groups"] == 0
+        for k in (2, 4):
+            got, stk = run(plan, lst, k)
+            assert 0 < stk["cross_groups"] <= stk["points"]
+            assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(base, got)), "group=%d" % k
+    auto, sta = run(plan, dense, None)
+    assert 0 < sta["cross_groups"] < 0.5 * sta["points"]          # ~3.5 per pair -> K = 4
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(run(plan, dense, 1)[0], auto))
+    _, sts = run(plan, w["index"][::7], None)                       # thinned list: nearly every pair once -> plain kernel
+    assert sts["cross_groups"] == 0
+    plan.close()
+    old = os.environ.get("SXS_CUDA_X_GB")
+    os.environ["SXS_CUDA_X_GB"] = "0.002"                           # ~1000 points per chunk: chunk boundaries cut runs
+    try:
+        small = capi.Plan(L, q)
+        small.set_molecules(A, B)
+        small.set_experiment(a, scal[1], scal[2])
+        small.set_translations(w["zvals"])
+        sub = dense[:30000]
+        b1_, _ = run(small, sub, 1)
+        for k in (2, 4):
+            gk, _ = run(small, sub, k)
+            assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(b1_, gk))
+        small.close()
+    finally:
+        if old is None:
+            os.environ.pop("SXS_CUDA_X_GB", None)
+        else:
+            os.environ["SXS_CUDA_X_GB"] = old
+
+
 def test_dense_scan_topk():
     """every grid point of one z step (16 x 16 cells x 31^3 = 7.6 M points) is scored on the device and
     the best 64 come back; they are what the list API gives for the same indices, and no sampled point beats them"""
