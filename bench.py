@@ -374,7 +374,7 @@ def pose_list_stats(idx, L):
             "rows_per_cell_max": int(counts.max())}
 
 
-TRAFFIC_FILE = "profiles/r1e_ncu_traffic.json"
+TRAFFIC_FILE = "profiles/r1f_ncu_traffic.json"
 
 
 def ncu_traffic(poses_per_gpu):

@@ -21,7 +21,7 @@ def main():
     per = OrderedDict()
     for r in rows:
         key = r[col["ID"]]
-        per.setdefault(key, {"name": r[col["Kernel Name"]].split("(")[0].split("<")[0].strip()})
+        per.setdefault(key, {"name": r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("void ", "").strip()})
         v = float(r[col["Metric Value"]].replace(",", ""))
         unit = r[col["Metric Unit"]]
         m = r[col["Metric Name"]]
