@@ -58,7 +58,7 @@ __host__ __device__ inline size_t sxs_x_index(long long p, int qnum, int q, int 
 
 /* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
 
-/* K4: one fit per point.  x: point-major cross terms, x[p*6*qnum + q*6 + k]; res[p*4] = chi, c1, c2,
+/* K4: one fit per point.  x: cross terms in the layout of sxs_x_index; res[p*4] = chi, c1, c2,
  * evaluations.  d_ticket: one device word used as the work queue head (reset by the launcher). */
 int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const double *d_qvals, int qnum, double mult,
                    double peak, int rescale, double *d_res, unsigned long long *d_ticket, cudaStream_t stream);

@@ -11,7 +11,7 @@
  * BEFORE the l-contraction, once per molecule and independent of z:
  *   At[b1][q][c][m,l][g1] = sum_m1 w^(m1 g1) d^l_{m m1}(b1)      A^c_{l m1}(q)        (k_rotate, receptor)
  *   Bt[b2][q][c][m,l][g2] = sum_m2 w^(m2 g2) d^l_{m m2}(b2) conj(B^c_{l m2}(q))       (k_rotate, ligand)
- *   St[z,b2][q][c][m,l][g2] = sum_l1 conj(T^m_{l l1}(q z)) Bt[b2][q][c][m,l1][g2]      (k_translate_tiled)
+ *   St[z,b2][q][c][m,l][g2] = sum_l1 conj(T^m_{l l1}(q z)) Bt[b2][q][c][m,l1][g2]      (k_translate_rt)
  * and what is left per listed pose (z, b1, b2, a2, g1, g2) is the alpha transform of a length-(L+1) dot:
  *   F_k = Re sum_m w^(m a2) sum_{l>=|m|} At^{c}[m,l,g1] St^{c'}[m,l,g2]                  (k_cross)
  * Only m >= 0 is evaluated: the m <-> -m terms are complex conjugates of each other (A_{l,-m} =
@@ -84,7 +84,7 @@ struct sxs_cuda_plan {
 	/* workspace (grow-only) */
 	double2 *d_T;  size_t cap_T;   /* [zg][q][m][l][l1] */
 	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g], rows padded like At */
-	double *d_X;   size_t cap_X;   /* [chunk][q][6] point-major rows */
+	double *d_X;   size_t cap_X;   /* cross terms handed from K3 to K4, tiles of 32 points (sxs_x_index) */
 	unsigned long long *d_ticket;
 	double *d_res; size_t cap_res; /* [points][4] */
 	unsigned long long *d_keys, *d_keys_sorted, *d_pkeys;
@@ -662,8 +662,8 @@ __device__ __forceinline__ void cmac(double2 &acc, const double2 a, const double
  * (k_make_keys), so a block mostly works inside one cell and a quarter warp inside one band of g2: its ligand
  * operands are 16-byte elements of one 128-byte line, its receptor operands those of a few neighbouring g1 —
  * served by L1/L2.
- * X[(p - p0)*6*qnum + q*6 + k] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108);
- * point-major rows, so that K4 streams one contiguous 6*qnum row per fit. */
+ * X[sxs_x_index(p - xbase, qnum, q, k)] = const_k[q] + 2 F_k   (fill_const + fill_var, src/fftsaxs.c:52-108), in tiles
+ * of 32 points so that a warp of K4 reads every term with one coalesced load. */
 /* [B200] 1.12 M points, (g1, g2, a2) order, 496-byte rows: 256x1 39.3 ms, 256x3 (80 regs, spills) 40.9, 128x4 38.4,
  * 128x5 45.1, 64x8 38.4, 512x1 41.1.  Band-major order + 512-byte rows: 128x4 36.1 (L1 data-pipe wavefronts per
  * 16-byte warp load 6.4 -> 4.2, the minimum: one per quarter warp); + next row requested before the MACs of the
