@@ -44,6 +44,20 @@ long long sxs_ft_rows_to_indices64(long long *index, int *ft_id, int *order, con
                                    const double *zvals, int znum, int L, int nthreads);
 long long sxs_euler_to_index64(const struct sxs_euler *euler, int z_index, int L);
 
+/* The whole file route of the tool in one threaded pass: reads the ft file once, writes the Euler side file
+ * (byte-identical to sxs_ft_file2euler_file's; eu_path may be NULL) and returns, for every row whose quantised z lies
+ * on zvals, what tools/correlate.c:202-251 would have read back from that file: *index (flat grid index, 64-bit),
+ * *ft_id (rotation index), *order (row number counting every row); the three arrays are malloc'ed here.  Returns the
+ * number of kept rows, or -1 without touching anything when the input is not plain enough for the fast parser (a row
+ * with other than ten tokens, a token fscanf would split differently, inf/nan/hex numbers): the caller then takes the
+ * slow route, which reports malformed files as the reference does. */
+long long sxs_ft_file_to_indices(const char *eu_path, const char *ft_path, const char *rm_path, struct mol_vector3 *ref_lig,
+                                 const double *zvals, int znum, int L, int nthreads, long long **index, int **ft_id,
+                                 int **order);
+/* Output rows of the tool, "%-6d\t%d\t%.3lf\t%.3lf\t%.3lf\n" (tools/correlate.c:369-375), formatted by nthreads threads. */
+void sxs_write_score_rows(const char *path, long long n, const int *order, const int *ft_id, const double *score,
+                          const double *c1, const double *c2, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

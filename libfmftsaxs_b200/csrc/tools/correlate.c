@@ -85,8 +85,16 @@ int main(int argc, char *argv[])
 	struct mol_vector3 ref_lig;
 	MOL_VEC_SUB(ref_lig, com, coe);
 	MOL_VEC_MULT_SCALAR(ref_lig, ref_lig, -1.0);
+	/* ft + rm -> Euler side file -> grid indices.  The fast route reads the ft file once with all host threads and gives
+	 * the same side file and the same indices as the three passes of the reference (index.h); files it does not take
+	 * go through those three passes below. */
 	SXS_PRINTF("Converting FT and RM files into Euler coordinates ...\n");
-	sxs_ft_file2euler_file(eul_path, ft_path, rm_path, &ref_lig);
+	long long *index64 = NULL;
+	int *ft_id = NULL, *order = NULL;
+	long long nfast = sxs_ft_file_to_indices(eul_path, ft_path, rm_path, &ref_lig, zvals, znum, L, 0, &index64, &ft_id, &order);
+	if (nfast < 0) {
+		sxs_ft_file2euler_file(eul_path, ft_path, rm_path, &ref_lig);
+	}
 
 	SXS_PRINTF("Reading experiment ...\n");
 	struct sxs_profile *exp_profile = sxs_profile_read(exp_path);
@@ -102,37 +110,50 @@ int main(int argc, char *argv[])
 	mol_atom_group_free(lig);
 
 	/* Euler rows -> grid indices; rows off the z table are dropped, serial numbers count every line */
+	size_t n = 0;
+	int *index = NULL;
 	SXS_PRINTF("Reading Euler coordinates ...\n");
-	FILE *ef = fopen(eul_path, "r");
-	if (ef == NULL) {
-		ERROR_MSG("cannot reopen Euler file");
-	}
-	size_t cap = 1 << 16, n = 0;
-	int *index = (int *)malloc(cap * sizeof(int)), *ft_id = (int *)malloc(cap * sizeof(int)),
-	    *order = (int *)malloc(cap * sizeof(int));
-	struct sxs_euler e;
-	int id, line = 0;
-	while (fscanf(ef, "%d %lf %lf %lf %lf %lf %lf", &id, &e.z, &e.b1, &e.g1, &e.a2, &e.b2, &e.g2) != EOF) {
-		for (int j = 0; j < znum; j++) {
-			if (zvals[j] > e.z - 0.001 && zvals[j] < e.z + 0.001) {
-				if (n == cap) {
-					cap *= 2;
-					index = (int *)realloc(index, cap * sizeof(int));
-					ft_id = (int *)realloc(ft_id, cap * sizeof(int));
-					order = (int *)realloc(order, cap * sizeof(int));
-					CHECK_PTR(index); CHECK_PTR(ft_id); CHECK_PTR(order);
-				}
-				index[n] = sxs_euler_to_index(&e, j, L);
-				ft_id[n] = id;
-				order[n] = line;
-				n++;
-				/* the reference reflects a2/g2 in place inside this loop, so a second matching z would see the
-				 * reflected angles; with the 1 Å table at most one z matches */
-			}
+	if (nfast >= 0) {
+		n = (size_t)nfast;
+		index = (int *)malloc((n ? n : 1) * sizeof(int));
+		CHECK_PTR(index);
+		for (size_t i = 0; i < n; i++) {
+			index[i] = (int)index64[i]; /* 32-bit packing like the tool's `int id` (tools/correlate.c:225-240) */
 		}
-		line++;
+		free(index64);
+	} else {
+		FILE *ef = fopen(eul_path, "r");
+		if (ef == NULL) {
+			ERROR_MSG("cannot reopen Euler file");
+		}
+		size_t cap = 1 << 16;
+		index = (int *)malloc(cap * sizeof(int));
+		ft_id = (int *)malloc(cap * sizeof(int));
+		order = (int *)malloc(cap * sizeof(int));
+		struct sxs_euler e;
+		int id, line = 0;
+		while (fscanf(ef, "%d %lf %lf %lf %lf %lf %lf", &id, &e.z, &e.b1, &e.g1, &e.a2, &e.b2, &e.g2) != EOF) {
+			for (int j = 0; j < znum; j++) {
+				if (zvals[j] > e.z - 0.001 && zvals[j] < e.z + 0.001) {
+					if (n == cap) {
+						cap *= 2;
+						index = (int *)realloc(index, cap * sizeof(int));
+						ft_id = (int *)realloc(ft_id, cap * sizeof(int));
+						order = (int *)realloc(order, cap * sizeof(int));
+						CHECK_PTR(index); CHECK_PTR(ft_id); CHECK_PTR(order);
+					}
+					index[n] = sxs_euler_to_index(&e, j, L);
+					ft_id[n] = id;
+					order[n] = line;
+					n++;
+					/* the reference reflects a2/g2 in place inside this loop, so a second matching z would see the
+					 * reflected angles; with the 1 Å table at most one z matches */
+				}
+			}
+			line++;
+		}
+		fclose(ef);
 	}
-	fclose(ef);
 
 	double *score = (double *)calloc(n ? n : 1, sizeof(double));
 	double *c1 = (double *)calloc(n ? n : 1, sizeof(double));
@@ -142,14 +163,7 @@ int main(int argc, char *argv[])
 
 	printf("\nTime passed: %.3f\n", (double)(clock() - t0) / CLOCKS_PER_SEC);
 	printf("Writing results to %s\n", out_path);
-	FILE *out = fopen(out_path, "w");
-	if (out == NULL) {
-		ERROR_MSG("cannot open output file");
-	}
-	for (size_t i = 0; i < n; i++) {
-		fprintf(out, "%-6d\t%d\t%.3lf\t%.3lf\t%.3lf\n", order[i], ft_id[i], score[i], c1[i], c2[i]);
-	}
-	fclose(out);
+	sxs_write_score_rows(out_path, (long long)n, order, ft_id, score, c1, c2, 0);
 	printf("\nCorrelation finished\n");
 
 	free(score); free(c1); free(c2); free(index); free(ft_id); free(order);

@@ -235,6 +235,88 @@ def test_ft_rows_in_memory_equals_the_euler_file_route(capi, tmp_path):
         assert open(eu_ref, "rb").read() == open(eu, "rb").read()
 
 
+def test_ft_file_fast_route_equals_the_three_pass_route(capi, tmp_path):
+    """sxs_ft_file_to_indices (one threaded pass over the ft file) writes the Euler side file of sxs_ft_file2euler_file
+    byte for byte and returns the (index, ft id, serial number) the tool reads back from it; files the fast parser
+    does not take are refused (-1) untouched; sxs_write_score_rows prints the tool's output format"""
+    rng = np.random.default_rng(12)
+    L, nrot, nrows = 15, 300, 20000
+    R, rot_id, trans, ref_lig = _random_ft_case(rng, nrot, nrows)
+    zvals = np.arange(1.0, 80.001, 1.0)
+    ft, rm, eu, eu2 = tmp_path / "ft.000.00", tmp_path / "rot.prm", tmp_path / "euler.txt", tmp_path / "euler_fast.txt"
+    with open(ft, "w") as f:
+        for i in range(nrows):
+            f.write("%d %.3f %.3f %.3f 0.0 0 -1.5e-3 0.0 0.0 0.0\n" % (rot_id[i], *trans[i]))
+    with open(rm, "w") as f:
+        for i in range(nrot):
+            f.write(" ".join("%.17g" % v for v in R[i]) + "\n")
+    capi.ft_file2euler_file(eu, ft, rm, ref_lig)
+    rows = np.loadtxt(eu)
+    zi = np.full(nrows, -1)
+    for j, zv in enumerate(zvals):
+        zi[(zv > rows[:, 1] - 0.001) & (zv < rows[:, 1] + 0.001)] = j
+    keep = zi >= 0
+    want_index = capi.euler_to_index(rows[keep, 1:], zi[keep].astype(np.int32), L).astype(np.int64)
+
+    lib = capi.lib()
+    LLP, IP = ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)
+    lib.sxs_ft_file_to_indices.restype = ctypes.c_longlong
+    lib.sxs_ft_file_to_indices.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double),
+                                           ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.POINTER(LLP), ctypes.POINTER(IP), ctypes.POINTER(IP)]
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+
+    def fast(ft_path, eu_path, nthreads):
+        v = (ctypes.c_double * 3)(*ref_lig)
+        z = (ctypes.c_double * len(zvals))(*zvals)
+        pi, pf, po = LLP(), IP(), IP()
+        n = lib.sxs_ft_file_to_indices(str(eu_path).encode() if eu_path else None, str(ft_path).encode(), str(rm).encode(), v, z,
+                                       len(zvals), L, nthreads, ctypes.byref(pi), ctypes.byref(pf), ctypes.byref(po))
+        if n < 0:
+            return None
+        out = (np.ctypeslib.as_array(pi, (max(n, 1),))[:n].copy(), np.ctypeslib.as_array(pf, (max(n, 1),))[:n].copy(),
+               np.ctypeslib.as_array(po, (max(n, 1),))[:n].copy())
+        for q in (pi, pf, po):
+            libc.free(ctypes.cast(q, ctypes.c_void_p))
+        return out
+
+    for nthreads in (1, 5, 0):
+        if os.path.exists(eu2):
+            os.remove(eu2)
+        index, ft_id, order = fast(ft, eu2, nthreads)
+        assert open(eu2, "rb").read() == open(eu, "rb").read()
+        assert 0 < len(index) < nrows
+        assert np.array_equal(order, np.flatnonzero(keep)) and np.array_equal(ft_id, rot_id[keep])
+        assert np.array_equal(index, want_index)
+    assert fast(ft, None, 2) is not None and all(np.array_equal(a, b) for a, b in zip(fast(ft, None, 2), (index, ft_id, order)))
+    # rows the fast parser must not interpret: a token fscanf would split, nan, a short last row
+    for bad in ("3 1.0 2.0 3.0 0 0 0 0 0 0\n4.5 1.0 2.0 3.0 0 0 0 0 0 0\n", "3 nan 2.0 3.0 0 0 0 0 0 0\n", "3 1.0 2.0 3.0 0 0 0 0 0\n"):
+        odd = tmp_path / "odd.ft"
+        open(odd, "w").write(bad)
+        marker = tmp_path / "untouched.txt"
+        open(marker, "w").write("keep")
+        assert fast(odd, marker, 2) is None
+        assert open(marker).read() == "keep"
+    # rows may be spread over lines differently: fscanf does not care, neither does the fast route
+    text = open(ft).read().split("\n")
+    open(tmp_path / "wrapped.ft", "w").write("\n".join(l.replace(" 0.0 0 ", " 0.0\n0 ", 1) for l in text))
+    w_index, w_ft_id, w_order = fast(tmp_path / "wrapped.ft", None, 1)
+    assert np.array_equal(w_index, index) and np.array_equal(w_order, order)
+
+    lib.sxs_write_score_rows.restype = None
+    lib.sxs_write_score_rows.argtypes = [ctypes.c_char_p, ctypes.c_longlong, IP, IP] + [ctypes.POINTER(ctypes.c_double)] * 3 + [ctypes.c_int]
+    n = 5000
+    o = np.arange(n, dtype=np.int32) * 3
+    fi = rng.integers(0, 70000, n).astype(np.int32)
+    sc, a1, a2 = rng.uniform(0, 50, n), rng.uniform(0.96, 1.04, n), rng.uniform(-2, 4, n)
+    for nthreads in (1, 3):
+        lib.sxs_write_score_rows(str(tmp_path / "rows.txt").encode(), n, o.ctypes.data_as(IP), fi.ctypes.data_as(IP),
+                                 capi.dptr(sc), capi.dptr(a1), capi.dptr(a2), nthreads)
+        want = "".join("%-6d\t%d\t%.3f\t%.3f\t%.3f\n" % (o[i], fi[i], sc[i], a1[i], a2[i]) for i in range(n))
+        assert open(tmp_path / "rows.txt").read() == want
+
+
 # ------------------------------------------------------------------ C ABI
 
 def test_c_abi_exports_every_declared_symbol(capi):
