@@ -112,15 +112,23 @@ int main(int argc, char *argv[])
 	/* Euler rows -> grid indices; rows off the z table are dropped, serial numbers count every line */
 	size_t n = 0;
 	int *index = NULL;
+	/* The reference packs the six digits into an `int` (tools/correlate.c:225-240), which overflows from L = 20 on with
+	 * the 80-step z table ((L+1)^2 (2L+1)^3 * 80 > 2^31): its rows are then wrong.  Where 32 bits suffice this tool
+	 * does exactly what the reference does; beyond that it keeps the 64-bit indices of the fast route. */
+	const double index_space = (double)znum * (L + 1) * (L + 1) * (2.0 * L + 1) * (2.0 * L + 1) * (2.0 * L + 1);
+	const int wide = nfast >= 0 && index_space > 2147483647.0;
 	SXS_PRINTF("Reading Euler coordinates ...\n");
-	if (nfast >= 0) {
+	if (wide) {
+		n = (size_t)nfast;
+	} else if (nfast >= 0) {
 		n = (size_t)nfast;
 		index = (int *)malloc((n ? n : 1) * sizeof(int));
 		CHECK_PTR(index);
 		for (size_t i = 0; i < n; i++) {
-			index[i] = (int)index64[i]; /* 32-bit packing like the tool's `int id` (tools/correlate.c:225-240) */
+			index[i] = (int)index64[i];
 		}
 		free(index64);
+		index64 = NULL;
 	} else {
 		FILE *ef = fopen(eul_path, "r");
 		if (ef == NULL) {
@@ -159,14 +167,18 @@ int main(int argc, char *argv[])
 	double *c1 = (double *)calloc(n ? n : 1, sizeof(double));
 	double *c2 = (double *)calloc(n ? n : 1, sizeof(double));
 	SXS_PRINTF("\nCORRELATION STARTED\n\n");
-	sxs_compute_saxs_scores(score, c1, c2, index, (int)n, A, B, params, qvals, qnum, zvals, znum, L, 1);
+	if (wide) {
+		sxs_compute_saxs_scores64(score, c1, c2, index64, (long long)n, A, B, params, qvals, qnum, zvals, znum, L, 1);
+	} else {
+		sxs_compute_saxs_scores(score, c1, c2, index, (int)n, A, B, params, qvals, qnum, zvals, znum, L, 1);
+	}
 
 	printf("\nTime passed: %.3f\n", (double)(clock() - t0) / CLOCKS_PER_SEC);
 	printf("Writing results to %s\n", out_path);
 	sxs_write_score_rows(out_path, (long long)n, order, ft_id, score, c1, c2, 0);
 	printf("\nCorrelation finished\n");
 
-	free(score); free(c1); free(c2); free(index); free(ft_id); free(order);
+	free(score); free(c1); free(c2); free(index); free(index64); free(ft_id); free(order);
 	sxs_opt_params_free(params);
 	sxs_spf_full_free(A);
 	sxs_spf_full_free(B);

@@ -148,3 +148,26 @@ def test_reference_tool_sources_run_on_the_product_library(files):
     subprocess.run([os.path.join(REF, "ref_single_saxs")] + s_common + [str(d / "p_ref2")], check=True, stdout=subprocess.DEVNULL)
     a, b = np.loadtxt(d / "p_drop"), np.loadtxt(d / "p_ref2")
     assert a.shape == b.shape == (50, 3) and np.max(np.abs(a[:, 1] / b[:, 1] - 1)) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_correlate")), reason="compiled reference tools not present")
+def test_correlate_cli_keeps_64_bit_indices_where_int_overflows(files):
+    """L = 20 with the 80-step z table needs more than 31 bits for the flat index; the tool then keeps 64-bit indices
+    (the reference's `int` packing is still right for z < 70, which is where these rows are): same rows as the reference"""
+    d = files
+    rows = open(d / "ft.000").read().splitlines()[:16]
+    with open(d / "ft.l20", "w") as f:
+        f.write("\n".join(rows) + "\n")
+    common = [MAP, PRM, str(d / "ft.l20"), str(d / "rot.prm"), str(d / "rec.pdb"), str(d / "lig.pdb"), str(d / "exp.dat"), "20"]
+    subprocess.run([os.path.join(BIN, "correlate")] + common + [str(d / "eul20_ours"), str(d / "out20_ours")], check=True,
+                   stdout=subprocess.DEVNULL, timeout=600)
+    subprocess.run([os.path.join(REF, "ref_correlate")] + common + [str(d / "eul20_ref"), str(d / "out20_ref")], check=True,
+                   stdout=subprocess.DEVNULL, timeout=1500)
+    assert open(d / "eul20_ours").read() == open(d / "eul20_ref").read()
+    ours = [l.split("\t") for l in open(d / "out20_ours").read().splitlines()]
+    ref = [l.split("\t") for l in open(d / "out20_ref").read().splitlines()]
+    assert len(ours) == len(ref) and len(ours) >= 5
+    for a, b in zip(ours, ref):
+        assert a[0].strip() == b[0].strip() and a[1] == b[1]
+        for x, y in zip(a[2:], b[2:]):
+            assert abs(float(x) - float(y)) <= 1.001e-3
