@@ -37,6 +37,38 @@ __host__ __device__ inline int sxs_ml_index(int L, int m, int l) { return m * (L
  * so that the 8 values g = 8k .. 8k+7 — one "band" — are exactly one cache line. */
 __host__ __device__ inline int sxs_row_pad(int N) { return (N + 7) & ~7; }
 
+/* Sort key of a pose (z, b1, b2, a2, g1, g2 = the digits of the reference's flat index, src/index.c:9-29):
+ * (z, b2, b1, g2 / 8, g1, g2 % 8, a2), most significant first.  Cells (z, b2, b1) are contiguous key ranges of
+ * sxs_keys_per_cell(N) keys, points that differ only in a2 are neighbours (key / N equal), and inside a cell the
+ * 128-byte band g2 / 8 of the ligand operand comes first. */
+struct sxs_pose_digits {
+	int z, b1, b2, a2, g1, g2;
+};
+__host__ __device__ inline unsigned long long sxs_keys_per_cell(int N)
+{
+	return (unsigned long long)(sxs_row_pad(N) / 8) * N * 8 * N;
+}
+__host__ __device__ inline unsigned long long sxs_key_pack(int nb, int N, const sxs_pose_digits &d)
+{
+	const unsigned long long nband = sxs_row_pad(N) / 8;
+	unsigned long long key = ((unsigned long long)d.z * nb + d.b2) * nb + d.b1;
+	key = ((key * nband + d.g2 / 8) * N + d.g1) * 8 + d.g2 % 8;
+	return key * N + d.a2;
+}
+__host__ __device__ inline sxs_pose_digits sxs_key_unpack(int nb, int N, unsigned long long key)
+{
+	const int nband = sxs_row_pad(N) / 8;
+	sxs_pose_digits d;
+	d.a2 = (int)(key % N); key /= N;
+	d.g2 = (int)(key % 8); key /= 8;
+	d.g1 = (int)(key % N); key /= N;
+	d.g2 += 8 * (int)(key % nband); key /= nband;
+	d.b1 = (int)(key % nb); key /= nb;
+	d.b2 = (int)(key % nb);
+	d.z = (int)(key / nb);
+	return d;
+}
+
 /* Cross terms between K3 and K4.  SXS_X_TILED: points are kept in tiles of 32 (one warp of K4); inside a tile the
  * 6*qnum terms are term-major and the 32 points are the fastest index, X[((tile*qnum + q)*6 + k)*32 + lane] — the
  * warp of K4 that owns the tile reads every term with one coalesced 256-byte load.  Otherwise point-major rows

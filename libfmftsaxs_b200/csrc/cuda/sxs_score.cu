@@ -574,15 +574,16 @@ __global__ void k_make_keys(const IndexT *__restrict__ index, long long nout, in
 	long long v = (long long)index[i];
 	unsigned long long key = SXS_KEY_NONE;
 	if (v >= 0) {
-		const long long g2 = v % N; v /= N;
-		const long long g1 = v % N; v /= N;
-		const long long a2 = v % N; v /= N;
-		const long long b2 = v % nb; v /= nb;
-		const long long b1 = v % nb;
+		sxs_pose_digits d;
+		d.g2 = (int)(v % N); v /= N;
+		d.g1 = (int)(v % N); v /= N;
+		d.a2 = (int)(v % N); v /= N;
+		d.b2 = (int)(v % nb); v /= nb;
+		d.b1 = (int)(v % nb);
 		const long long z = v / nb;
 		if (z >= z_lo && z < z_hi) {
-			const long long nband = sxs_row_pad(N) / 8;
-			key = (unsigned long long)(((((((z * nb + b2) * nb + b1) * nband + g2 / 8) * N + g1) * 8 + g2 % 8) * N) + a2);
+			d.z = (int)z;
+			key = sxs_key_pack(nb, N, d);
 		}
 	}
 	keys[i] = key;
@@ -711,6 +712,7 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 	}
 	const int q = blockIdx.y;
 	const int NP = sxs_row_pad(N), nband = NP / 8;
+	/* the digits of sxs_key_unpack, spelled out: this order of the divisions keeps the kernel at 108 / 122 registers */
 	unsigned long long key = pkeys[p];
 	int a2[K];
 	a2[0] = (int)(key % N); key /= N;
@@ -1065,7 +1067,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	if (np == 0) {
 		return 0;
 	}
-	const unsigned long long per_cell = (unsigned long long)(sxs_row_pad(N) / 8) * N * 8 * N; /* keys per (z, b2, b1) */
+	const unsigned long long per_cell = sxs_keys_per_cell(N); /* keys per (z, b2, b1) */
 	const unsigned long long per_zb2 = (unsigned long long)nb * per_cell;
 	const unsigned long long per_z = per_zb2 * nb;
 	k_z_offsets<<<(znum + 2 + 127) / 128, 128, 0, st>>>(p->d_pkeys, np, p->d_keys_sorted, nout, znum, per_z, p->d_zoff);

@@ -317,6 +317,24 @@ def test_ft_file_fast_route_equals_the_three_pass_route(capi, tmp_path):
         assert open(tmp_path / "rows.txt").read() == want
 
 
+def test_device_index_arithmetic_on_the_host(tmp_path):
+    """sxs_dev.cuh: sort key pack/unpack round trip, cells as contiguous key ranges in (z, b2, b1) order, a2 runs adjacent,
+    ligand band as the leading digit inside a cell, 64-bit range; tiled K3 -> K4 layout is a bijection with the 32
+    points of a tile fastest (tests/cpu_harness/layout_host.cu, compiled by nvcc, runs without a GPU)"""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not present")
+    exe = tmp_path / "layout_host"
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-Wno-deprecated-gpu-targets", "-I" + os.path.join(REPO, "include"),
+                        "-I" + os.path.join(REPO, "include", "fmftsaxs"), "-I" + os.path.join(REPO, "libfmftsaxs_b200", "csrc", "cuda"),
+                        os.path.join(HERE, "cpu_harness", "layout_host.cu"), "-o", str(exe)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout
+
+
 # ------------------------------------------------------------------ C ABI
 
 def test_c_abi_exports_every_declared_symbol(capi):
