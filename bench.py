@@ -327,8 +327,12 @@ def run_product(args):
         def roof(name, flops_per_step, ms_total, launches):
             ach = flops_per_step * args.steps / (ms_total * 1e-3) / 1e12 if ms_total > 0 else None
             key = name.split(" ")[0]
+            dram = traffic.get(key)
             return {"kernel": name, "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": (ach / fp64_peak) if ach else None, "traffic": traffic.get(key), "peak_source": peak_src,
+                    "frac": (ach / fp64_peak) if ach else None, "traffic": dram, "peak_source": peak_src,
+                    # measured DRAM bytes per launch over the live launch time, beside the copy bandwidth of MEASURED_PEAKS.json
+                    "dram_gbs": (dram / (ms_total / max(1, launches) * 1e-3) / 1e9) if (dram and ms_total > 0) else None,
+                    "hbm_peak_gbs": hbm_peak(),
                     "traffic_source": TRAFFIC_FILE if key in traffic else None,
                     "flops_per_launch": flops_per_step / max(1, launches // args.steps),
                     "avg_launch_ms": ms_total / max(1, launches), "ms_per_step": ms_total / args.steps}
@@ -375,6 +379,13 @@ def pose_list_stats(idx, L):
 
 
 TRAFFIC_FILE = "profiles/r1f_ncu_traffic.json"
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except (OSError, ValueError):
+        return None
 
 
 def ncu_traffic(poses_per_gpu):
