@@ -71,17 +71,19 @@ void sxs_fill_active_rotation_matrix(struct mol_matrix3 *rm, double alpha, doubl
 	rm->m33 = cb;
 }
 
+/* c = a b (src/saxs_utils.c:81-94).  mol_matrix3 is nine consecutive doubles in row-major order; every entry is the
+ * left-to-right sum of its three products, and c may alias a or b. */
 void sxs_mult_rot_mats(struct mol_matrix3 *c, struct mol_matrix3 *a, struct mol_matrix3 *b)
 {
-	struct mol_matrix3 r;
-	r.m11 = a->m11 * b->m11 + a->m12 * b->m21 + a->m13 * b->m31;
-	r.m12 = a->m11 * b->m12 + a->m12 * b->m22 + a->m13 * b->m32;
-	r.m13 = a->m11 * b->m13 + a->m12 * b->m23 + a->m13 * b->m33;
-	r.m21 = a->m21 * b->m11 + a->m22 * b->m21 + a->m23 * b->m31;
-	r.m22 = a->m21 * b->m12 + a->m22 * b->m22 + a->m23 * b->m32;
-	r.m23 = a->m21 * b->m13 + a->m22 * b->m23 + a->m23 * b->m33;
-	r.m31 = a->m31 * b->m11 + a->m32 * b->m21 + a->m33 * b->m31;
-	r.m32 = a->m31 * b->m12 + a->m32 * b->m22 + a->m33 * b->m32;
-	r.m33 = a->m31 * b->m13 + a->m32 * b->m23 + a->m33 * b->m33;
-	*c = r;
+	const double *x = &a->m11, *y = &b->m11;
+	double r[9];
+	for (int row = 0; row < 3; row++) {
+		for (int col = 0; col < 3; col++) {
+			r[3 * row + col] = x[3 * row] * y[col] + x[3 * row + 1] * y[3 + col] + x[3 * row + 2] * y[6 + col];
+		}
+	}
+	double *out = &c->m11;
+	for (int k = 0; k < 9; k++) {
+		out[k] = r[k];
+	}
 }
