@@ -52,6 +52,14 @@ def lib():
         _lib.sxs_cuda_plan_set_profiling.argtypes = [C.c_void_p, C.c_int]
         _lib.sxs_cuda_plan_kernel_times.argtypes = [C.c_void_p, _dp, _llp]
         _lib.sxs_cuda_plan_cross_terms_i32.argtypes = [C.c_void_p, _ip, C.c_longlong, _dp]
+        _lib.sxs_cuda_plan_scan_topk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _llp, _dp, _dp, _dp]
+        for f in (_lib.sxs_cuda_plan_set_molecules, _lib.sxs_cuda_plan_set_experiment, _lib.sxs_cuda_plan_set_translations,
+                  _lib.sxs_cuda_plan_score_i32, _lib.sxs_cuda_plan_score_i64, _lib.sxs_cuda_plan_score_dev_i32,
+                  _lib.sxs_cuda_plan_score_dev_i64, _lib.sxs_cuda_plan_stats, _lib.sxs_cuda_plan_fit_evaluations,
+                  _lib.sxs_cuda_plan_set_profiling, _lib.sxs_cuda_plan_kernel_times, _lib.sxs_cuda_plan_cross_terms_i32,
+                  _lib.sxs_cuda_plan_scan_topk):
+            f.restype = C.c_int
+        _lib.sxs_cuda_plan_destroy.restype = None
         _lib.sxs_sbessel.restype = C.c_double
         _lib.sxs_sbessel.argtypes = [C.c_int, C.c_double]
         _lib.sxs_wigner_3j.restype = C.c_double

@@ -33,8 +33,9 @@
 
 /* ------------------------------------------------------------------ errors */
 
-/* process-wide: the device threads of a multi-GPU call report through the thread that joins them */
-static char g_err[512] = "no error";
+/* one buffer per host thread: the device threads of a multi-GPU call each keep their own message, and the host
+ * layer copies it into the shard job before the thread ends (csrc/host/fftsaxs.c) */
+static thread_local char g_err[512] = "no error";
 
 extern "C" void sxs_cuda_set_error(const char *fmt, ...)
 {

@@ -29,7 +29,11 @@ int sxs_host_device_list(int *devices, int cap)
 			if (end == p) {
 				break;
 			}
-			if (v >= 0 && v < visible) {
+			int seen = 0;
+			for (int k = 0; k < n; k++) {
+				seen |= devices[k] == (int)v; /* a device named twice is one device: its plan is not shareable */
+			}
+			if (v >= 0 && v < visible && !seen) {
 				devices[n++] = (int)v;
 			}
 			p = (*end == ',') ? end + 1 : end;
@@ -97,6 +101,7 @@ struct shard_job {
 	long long nout;
 	double *scores, *c1, *c2;
 	int rc;
+	char err[512]; /* the CUDA layer's message of this thread (its error buffer is thread-local) */
 };
 
 static void *shard_main(void *arg)
@@ -112,8 +117,15 @@ static void *shard_main(void *arg)
 			j->rc = sxs_cuda_plan_score_i64(j->plan, j->idx64, j->nout, j->z_lo, j->z_hi, j->scores, j->c1, j->c2);
 		}
 	}
+	if (j->rc != 0) {
+		snprintf(j->err, sizeof(j->err), "%s", sxs_cuda_last_error());
+	}
 	return NULL;
 }
+
+/* The plan cache and the per-device plans are process-wide state: concurrent callers take turns (the reference
+ * itself is non-reentrant, SURVEY 8b "Threading"). */
+static pthread_mutex_t g_score_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static void score_impl(double *scores, double *c1, double *c2, const int *idx32, const long long *idx64,
                        long long nout, struct sxs_spf_full *A, struct sxs_spf_full *B, struct sxs_opt_params *params,
@@ -125,6 +137,7 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	if (nout <= 0 || znum <= 0) {
 		return;
 	}
+	pthread_mutex_lock(&g_score_lock);
 	const struct sxs_l_tables *t = sxs_l_tables_get(L);
 	const int N = 2 * L + 1, nb = L + 1;
 
@@ -210,7 +223,7 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	}
 	for (int k = 0; k < njobs; k++) {
 		if (jobs[k].rc != 0) {
-			fprintf(stderr, "[Error] sxs_compute_saxs_scores: CUDA layer failed: %s\n", sxs_cuda_last_error());
+			fprintf(stderr, "[Error] sxs_compute_saxs_scores: CUDA layer failed: %s\n", jobs[k].err);
 			exit(EXIT_FAILURE);
 		}
 	}
@@ -218,6 +231,7 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	free(bessel);
 	free(coefA);
 	free(coefB);
+	pthread_mutex_unlock(&g_score_lock);
 }
 
 void sxs_compute_saxs_scores(double *scores_list, double *c1_list, double *c2_list, int *index_list, int nout,
