@@ -124,10 +124,26 @@ def sample_slabs(index, L, nslabs, seed=7):
     nb, N = L + 1, 2 * L + 1
     v = index.astype(np.int64) // (N ** 3)          # (z*nb + b1)*nb + b2
     slab = (v // (nb * nb)) * nb + (v % nb)          # z*nb + b2
+    if L > 20:
+        # one L = 30 cell costs the reference ~25 s: the bounded sample is made of single cells there
+        slab = v
     u = np.unique(slab)
     rng = np.random.default_rng(seed)
     pick = rng.choice(u, size=min(nslabs, len(u)), replace=False)
     return [np.flatnonzero(slab == s) for s in pick]
+
+
+def to_ref_index(index, zvals, L):
+    """the reference takes 32-bit flat indices (src/fftsaxs.h:99): trim the z table to the z steps these poses use and
+    renumber the z digit, so that any sample of an L = 30 list fits; values of z, and every other digit, stay"""
+    nb, N = L + 1, 2 * L + 1
+    idx64 = np.asarray(index).astype(np.int64)
+    per_z = nb * nb * N ** 3
+    zu = np.unique(idx64 // per_z)
+    idx = np.searchsorted(zu, idx64 // per_z) * per_z + idx64 % per_z
+    if len(idx) and idx.max() >= 2 ** 31:
+        raise ValueError("sample spans too many z steps for the reference's 32-bit index")
+    return idx.astype(np.int32), np.asarray(zvals)[zu]
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
@@ -135,8 +151,9 @@ def sample_slabs(index, L, nslabs, seed=7):
 def _ref_worker(job):
     import refso
     idx, w = job
+    idx, zv = to_ref_index(idx, w["zvals"], w["L"])
     t = time.perf_counter()
-    refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], w["zvals"], w["L"])
+    refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], zv, w["L"])
     return time.perf_counter() - t
 
 
@@ -342,7 +359,7 @@ def run_product(args):
         r_fit = roof("k_fit (K4: fused (c1,c2) fit)", fit_flops, fit_ms, fit_n)
         r_fit["evaluations_per_fit"] = nfg_mean
         roofline, roofline2 = (r_fit, r_cross) if fit_ms >= cross_ms else (r_cross, r_fit)
-        cpu = cpu_baseline(w, args)
+        cpu, parity_line = cpu_baseline(w, args, d_out)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -360,7 +377,10 @@ def run_product(args):
                                     "p99": int(np.searchsorted(np.cumsum(hist), 0.99 * hist.sum())),
                                     "max_bin": int(np.flatnonzero(hist).max()) if hist.sum() else 0},
                 "pose_list": pose_list_stats(idx, L),
-                "roofline": roofline, "roofline_second_kernel": roofline2, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_second_kernel": roofline2, "cpu_baseline": cpu, "parity": parity_line,
+                "value_excludes": "plan set-up (rotated coefficient tables: k_rotate x2, 0.8 ms; L-only tables, cached per "
+                                  "process; j_p(qz) table) happens before the timed steps; the e2e leg calls "
+                                  "sxs_compute_saxs_scores, which includes it on every call",
                 "resident_equals_host_path": same}
         print(json.dumps(line))
     if world > 1:
@@ -400,20 +420,49 @@ def ncu_traffic(poses_per_gpu):
     return {k: v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"] for k, v in t["kernels"].items()}
 
 
-def cpu_baseline(w, args):
-    """the compiled reference on ONE host core over a bounded sample of the same poses (rank 0, N=1 only)"""
-    if env_int("WORLD_SIZE", 1) != 1 or args.no_cpu_baseline:
-        return None
+def _sens_worker(job):
     import refso
+    idx, w = job
+    return refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], w["zvals"], w["L"], so=refso.SENS_SO)
+
+
+def cpu_baseline(w, args, d_out):
+    """The compiled reference on ONE host core over a bounded sample of the same poses (rank 0, N=1 only) — and what
+    the reference says about those poses is compared with what the GPU just wrote for them (`parity`).  Beside it,
+    `reference_self_noise`: the same sample scored by the reference's own sources built with FMA contraction
+    (oracle/Makefile, libsxsref_fma.so), i.e. how far the reference is from itself under a 1e-16 perturbation."""
+    if env_int("WORLD_SIZE", 1) != 1 or args.no_cpu_baseline:
+        return None, None
+    import refso
+    import parity
     if not refso.available():
-        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
-    idx = np.concatenate([w["index"][r] for r in sample_slabs(w["index"], w["L"], args.cpu_slabs)])
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}, None
+    L = w["L"]
+    rows = np.concatenate(sample_slabs(w["index"], L, args.cpu_slabs))
+    idx, zv = to_ref_index(w["index"][rows], w["zvals"], L)
+    small = dict(coefA=w["coefA"], coefB=w["coefB"], a=w["a"], scal=w["scal"], qvals=w["qvals"], zvals=zv, L=L)
+    pool = None
+    pending = None
+    if refso.sens_available() and not args.no_self_noise:
+        from multiprocessing import get_context
+        pool = get_context("spawn").Pool(1)
+        pending = pool.apply_async(_sens_worker, ((idx, small),))
     t = time.perf_counter()
-    refso.scores(idx, w["coefA"], w["coefB"], w["a"], w["scal"], w["qvals"], w["zvals"], w["L"])
+    want = refso.scores(idx, small["coefA"], small["coefB"], small["a"], small["scal"], small["qvals"], small["zvals"], L)
     dt = time.perf_counter() - t
-    return {"value": len(idx) / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
-            "sample": "all %d poses of %d random (z,beta2) slab(s) of the workload (up to L+1 complete cells each); "
-                      "unmodified reference sources, FFTW replaced by the DFT shim" % (len(idx), args.cpu_slabs)}
+    import torch
+    got = d_out[:, torch.from_numpy(rows).to(d_out.device)].cpu().numpy()
+    par = parity.summary((got[0], got[1], got[2]), want)
+    par["against"] = "compiled reference (oracle/_ref/libsxsref.so) on the cpu_baseline sample of the benchmarked list"
+    if pending is not None:
+        sens = pending.get()
+        pool.close()
+        noise = parity.summary(sens, want)
+        par["reference_self_noise"] = {k: noise[k] for k in ("max_rel_chi", "max_rel_c1", "max_rel_c2", "rows_over_tol")}
+    cpu = {"value": len(idx) / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
+           "sample": "all %d poses of %d random (z,beta2) slab(s) of the workload (up to L+1 complete cells each); "
+                     "unmodified reference sources, FFTW replaced by the DFT shim" % (len(idx), args.cpu_slabs)}
+    return cpu, par
 
 
 def main():
@@ -428,6 +477,7 @@ def main():
     ap.add_argument("--nz", type=int, default=None, help="override number of z steps (default 64)")
     ap.add_argument("--cpu-slabs", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-self-noise", action="store_true", help="skip the FMA-build leg of the parity report")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-slabs-per-proc", type=int, default=1)
     args = ap.parse_args()

@@ -1,0 +1,73 @@
+"""How (chi, c1, c2) of the CUDA path are compared with the reference's — one definition for tests/ and bench.py.
+
+north_star: SAXS-score, c1 and c2 within 1e-6 RELATIVE in FP64.  c2 lives in [-2, 4] and crosses zero, so its
+denominator is max(|c2_ref|, C2_FLOOR) with C2_FLOOR = 1e-3: below |c2| = 1e-3 the bound is 1e-9 absolute.
+
+The minimiser stops mid-convergence (factr = 1e7, pgtol = 1e-5), so (c1, c2) of single rows move when the arithmetic
+is perturbed at the 1e-16 level — the reference against ITSELF compiled with FMA contraction (oracle/Makefile,
+libsxsref_fma.so) differs by more than 1e-6 in c2 on about 1 row in 1000 of the real 4G9S list.
+`summary()` therefore reports the maxima, the number of rows beyond the tolerance and a per-decade histogram, and the
+tests bound the outlier COUNT next to the reference's own count instead of pretending it is zero.
+"""
+import numpy as np
+
+TOL = 1e-6
+C2_FLOOR = 1e-3
+DECADES = (1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3)
+
+
+def deviations(got, want):
+    """relative deviations of (chi, c1, c2); got/want = (scores, c1, c2) arrays"""
+    s, c1, c2 = (np.asarray(x, dtype=np.float64) for x in got)
+    rs, r1, r2 = (np.asarray(x, dtype=np.float64) for x in want)
+    ds = np.abs(s - rs) / np.maximum(np.abs(rs), 1e-300)
+    d1 = np.abs(c1 - r1) / np.maximum(np.abs(r1), 1e-300)
+    d2 = np.abs(c2 - r2) / np.maximum(np.abs(r2), C2_FLOOR)
+    return ds, d1, d2
+
+
+def summary(got, want, tol=TOL):
+    ds, d1, d2 = deviations(got, want)
+    n = len(ds)
+    if n == 0:
+        return {"rows": 0}
+    worst = np.maximum(np.maximum(ds, d1), d2)
+    hist = {("%.0e" % t): [int((d > t).sum()) for d in (ds, d1, d2)] for t in DECADES}
+    return {"rows": int(n), "tol": tol, "c2_floor": C2_FLOOR,
+            "max_rel_chi": float(ds.max()), "max_rel_c1": float(d1.max()), "max_rel_c2": float(d2.max()),
+            "max_abs_c2": float(np.max(np.abs(np.asarray(got[2]) - np.asarray(want[2])))),
+            "rows_over_tol": int((worst > tol).sum()),
+            "rows_over_tol_chi_c1_c2": [int((d > tol).sum()) for d in (ds, d1, d2)],
+            "rows_over_threshold_chi_c1_c2": hist}
+
+
+def fmt(tag, sm):
+    if sm.get("rows", 0) == 0:
+        return "%s: no rows" % tag
+    return ("%s: %d rows, max rel dchi %.2e dc1 %.2e dc2 %.2e (abs dc2 %.2e); rows beyond %.0e: %d (chi %d, c1 %d, c2 %d); "
+            "beyond 1e-7: %s, 1e-8: %s"
+            % (tag, sm["rows"], sm["max_rel_chi"], sm["max_rel_c1"], sm["max_rel_c2"], sm["max_abs_c2"], sm["tol"],
+               sm["rows_over_tol"], *sm["rows_over_tol_chi_c1_c2"], sm["rows_over_threshold_chi_c1_c2"]["1e-07"],
+               sm["rows_over_threshold_chi_c1_c2"]["1e-08"]))
+
+
+# ---- the acceptance rule of the -m gpu parity tests -------------------------------------------------------------
+# chi: every row within TOL (the minimum is flat, chi does not feel where on the valley floor the minimiser stops).
+# c1, c2: every row within TOL except at most OUTLIER_RATE of the rows — the rate at which the reference disagrees
+#         with its own FMA build on the real 4G9S list (1 of 1131 rows; tests/golden/make_golden_bench.py stores that
+#         build's answers next to the reference's) — and no outlier further than OUTLIER_CAP.
+OUTLIER_RATE = 1e-3
+OUTLIER_CAP = 1e-2
+
+
+def check(tag, got, want, rate=OUTLIER_RATE, cap=OUTLIER_CAP, sens=None):
+    sm = summary(got, want)
+    print(fmt(tag, sm))
+    if sens is not None:
+        print(fmt(tag + " [reference vs its own FMA build]", summary(sens, want)))
+    if sm["rows"] == 0:
+        return sm
+    assert sm["max_rel_chi"] < TOL, tag
+    assert sm["rows_over_tol"] <= int(rate * sm["rows"]), "%s: %d rows beyond %g" % (tag, sm["rows_over_tol"], TOL)
+    assert max(sm["max_rel_c1"], sm["max_rel_c2"]) < cap, tag
+    return sm

@@ -20,18 +20,27 @@ def available():
     return os.path.exists(REF_SO)
 
 
-_lib = None
+# the same unmodified sources compiled WITH FMA contraction (oracle/Makefile, target sens): not a second oracle but
+# the reference's own answer to a 1e-16-level perturbation of its arithmetic — the noise floor parity is read against
+SENS_SO = os.path.join(REPO, "oracle", "_ref", "libsxsref_fma.so")
+
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(REF_SO)
-        _lib.ref_sbessel.restype = C.c_double
-        _lib.ref_sbessel.argtypes = [C.c_int, C.c_double]
-        _lib.ref_wigner_3j.restype = C.c_double
-        _lib.ref_wigner_3j.argtypes = [C.c_int] * 6
-    return _lib
+def sens_available():
+    return os.path.exists(SENS_SO)
+
+
+def lib(path=None):
+    path = path or REF_SO
+    if path not in _libs:
+        l = C.CDLL(path)
+        l.ref_sbessel.restype = C.c_double
+        l.ref_sbessel.argtypes = [C.c_int, C.c_double]
+        l.ref_wigner_3j.restype = C.c_double
+        l.ref_wigner_3j.argtypes = [C.c_int] * 6
+        _libs[path] = l
+    return _libs[path]
 
 
 def dptr(a):
@@ -113,7 +122,7 @@ def opt_params(exp_q, exp_in, exp_err, qvals, rm):
     return a, scal
 
 
-def scores(index_list, coefA, coefB, a, scal, qvals, zvals, L, skip=1, init=None):
+def scores(index_list, coefA, coefB, a, scal, qvals, zvals, L, skip=1, init=None, so=None):
     idx = np.ascontiguousarray(index_list, dtype=np.int32)
     n = len(idx)
     s = np.zeros(n) if init is None else init[0].copy()
@@ -121,19 +130,19 @@ def scores(index_list, coefA, coefB, a, scal, qvals, zvals, L, skip=1, init=None
     c2 = np.zeros(n) if init is None else init[2].copy()
     qvals = np.ascontiguousarray(qvals, dtype=np.float64)
     zvals = np.ascontiguousarray(zvals, dtype=np.float64)
-    lib().ref_scores(dptr(s), dptr(c1), dptr(c2), iptr(idx), C.c_int(n), dptr(np.ascontiguousarray(coefA)),
+    lib(so).ref_scores(dptr(s), dptr(c1), dptr(c2), iptr(idx), C.c_int(n), dptr(np.ascontiguousarray(coefA)),
                      dptr(np.ascontiguousarray(coefB)), dptr(np.ascontiguousarray(a)), dptr(np.ascontiguousarray(scal)),
                      dptr(qvals), C.c_int(len(qvals)), dptr(zvals), C.c_int(len(zvals)), C.c_int(L), C.c_int(skip))
     return s, c1, c2
 
 
-def fit(x, a, scal, qvals, rescale=True):
+def fit(x, a, scal, qvals, rescale=True, so=None):
     """x: [npts][6][qnum] cross terms -> [npts][4] = score, c1, c2, nfg"""
     x = np.ascontiguousarray(x, dtype=np.float64)
     npts = x.shape[0]
     out = np.zeros((npts, 4))
     qvals = np.ascontiguousarray(qvals, dtype=np.float64)
-    lib().ref_fit(dptr(x), C.c_int(npts), dptr(np.ascontiguousarray(a)), dptr(np.ascontiguousarray(scal)),
+    lib(so).ref_fit(dptr(x), C.c_int(npts), dptr(np.ascontiguousarray(a)), dptr(np.ascontiguousarray(scal)),
                   dptr(qvals), C.c_int(len(qvals)), C.c_int(1 if rescale else 0), dptr(out))
     return out
 

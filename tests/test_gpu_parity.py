@@ -11,6 +11,7 @@ import pytest
 
 from libfmftsaxs_b200 import capi
 import refso
+import parity
 from golden import proto_cross_terms as proto
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -90,9 +91,8 @@ def test_fit_kernel_against_reference_lbfgsb(G, FC):
     X = np.concatenate([FC["X52"], proto.perturbed_family(FC["X52"], 4000, 1)])
     want = np.concatenate([FC["fit52"], FC["fit_family"]])
     got = capi.cuda_fit_profiles(X, a, q, scal[1], scal[2], rescale=True)
-    assert relmax(got[:, 0], want[:, 0]) < TOL
-    assert relmax(got[:, 1], want[:, 1]) < TOL
-    assert np.max(np.abs(got[:, 2] - want[:, 2])) < TOL * 4
+    parity.check("4052 fits", (got[:, 0], got[:, 1], got[:, 2]), (want[:, 0], want[:, 1], want[:, 2]))
+    print("identical evaluation counts: %.4f" % np.mean(got[:, 3] == want[:, 3]))
     # same trajectory for most fits: the kernel's one-pass objective (fit_eval.h, sxs_fit_eval_fused) equals the
     # reference's two-pass value up to rounding, which moves a line search by one evaluation now and then
     # (95.7 % identical counts here; 99.7 % with -DSXS_FIT_EVAL_EXACT, where only exp() differs in the last ulp).
@@ -119,9 +119,7 @@ def test_scores_z40_ref_chi(G):
     """score_conformations (tests/saxs_test.c:177-363) through sxs_compute_saxs_scores"""
     q, L = G["qvals"], int(G["L"])
     s, c1, c2 = capi.scores(G["z40_index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, [40.0], L)
-    assert relmax(s, G["z40_scores"]) < TOL
-    assert relmax(c1, G["z40_c1"]) < TOL
-    assert np.max(np.abs(c2 - G["z40_c2"])) < TOL * 4
+    parity.check("z = 40 golden rows", (s, c1, c2), (G["z40_scores"], G["z40_c1"], G["z40_c2"]))
     rc = G["ref_chi"]
     assert np.array_equal(rc[:, 0].astype(int), G["z40_ft"])
     assert np.max(np.abs(s - rc[:, 1])) < 1e-3
@@ -133,9 +131,7 @@ def test_scores_six_z_with_fft_branch_cells(G):
     """1131 real rows over 6 z steps; some cells hold >= 30 rows (the reference's FFTW branch)"""
     q, L = G["qvals"], int(G["L"])
     s, c1, c2 = capi.scores(G["z6_index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, G["z6_zvals"], L)
-    assert relmax(s, G["z6_scores"]) < TOL
-    assert relmax(c1, G["z6_c1"]) < TOL
-    assert np.max(np.abs(c2 - G["z6_c2"])) < TOL * 4
+    parity.check("six z steps", (s, c1, c2), (G["z6_scores"], G["z6_c1"], G["z6_c2"]))
 
 
 def test_scores_edge_cases(G):
@@ -186,6 +182,4 @@ def test_live_reference_random_rows(G):
     idx = (((((dig[:, 0] * nb + dig[:, 1]) * nb + dig[:, 2]) * N + dig[:, 3]) * N + dig[:, 4]) * N + dig[:, 5]).astype(np.int32)
     want = refso.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
     got = capi.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
-    assert relmax(got[0], want[0]) < TOL
-    assert relmax(got[1], want[1]) < TOL
-    assert np.max(np.abs(got[2] - want[2])) < TOL * 4
+    parity.check("live reference, 60 random grid points", got, want)
