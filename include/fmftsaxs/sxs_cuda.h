@@ -112,6 +112,10 @@ int sxs_cuda_fit_profiles(int device, const double *cross, long long npts, const
 int sxs_cuda_fit_eval(int device, const double *cross, const double *a, const double *qvals, int qnum, double mult,
                       double c1, double c2, double *out4);
 
+/* exp() as the objective evaluates it on the device (exp_glibc.h: the reference libm's algorithm), y[i] = exp(x[i]);
+ * host arrays.  Stage access for the parity tests. */
+int sxs_cuda_exp_array(int device, const double *x, long long n, double *y);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,6 +99,17 @@ def fp64_peak(device=0):
     return v.value
 
 
+def cuda_exp(x, device=0):
+    """exp() as the device evaluates it inside the objective (sxs_cuda_exp_array)"""
+    x = _c(x)
+    y = np.zeros_like(x)
+    f = lib().sxs_cuda_exp_array
+    f.argtypes = [C.c_int, _dp, C.c_longlong, _dp]
+    f.restype = C.c_int
+    _check(f(device, dptr(x), x.size, dptr(y)), "sxs_cuda_exp_array")
+    return y
+
+
 # ------------------------------------------------------------------ reference-shaped API (flat adapters)
 
 def mkarray(begin, end, n):

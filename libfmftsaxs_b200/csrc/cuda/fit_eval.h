@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stddef.h>
 
+#include "exp_glibc.h"
+
 #ifndef SXS_HD
 #ifdef __CUDACC__
 #define SXS_HD __host__ __device__ __forceinline__
@@ -33,7 +35,18 @@ struct sxs_fit_ctx {
 	double mult;          /* (4pi/3)^(3/2) rm^2 / (16 pi), src/min_saxs.c:121 */
 	double scale;         /* peak / I(0) rescale, src/min_saxs.c:170-179 */
 	const double *rq;     /* optional table rq[i] = 1/(q_i - q_{i-1}), q_{-1} = -1 (same IEEE quotient as in the loop) */
+	const uint64_t *etab; /* 2^(k/128) table of exp_glibc.h; NULL on the host = call libm's exp itself */
 };
+
+/* exp() of the objective: the reference's libm algorithm, bit for bit (exp_glibc.h) */
+SXS_HD double sxs_fit_exp(const struct sxs_fit_ctx *ctx, double x)
+{
+#ifdef __CUDA_ARCH__
+	return sxs_exp_glibc(x, ctx->etab);
+#else
+	return ctx->etab ? sxs_exp_glibc(x, ctx->etab) : exp(x);
+#endif
+}
 
 enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 
@@ -83,7 +96,7 @@ SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, doubl
 	const double *q = ctx->qvals;
 	const double mult = ctx->mult;
 	const double corr = -mult * (c1 * c1 - 1.0);
-	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
+	double G = c1 * c1 * c1 * sxs_fit_exp(ctx, corr * q[0] * q[0]);
 
 	double xvv, xvd, xvw, xdd, xdw, xww;
 	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
@@ -94,7 +107,7 @@ SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, doubl
 
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
-		G = c1_cube * exp(corr * q_cur * q_cur);
+		G = c1_cube * sxs_fit_exp(ctx, corr * q_cur * q_cur);
 		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
 		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 		const double tan = (in - in_prev) / (q_cur - q_prev);
@@ -119,7 +132,7 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 
 	double grad0 = 0.0, grad1 = 0.0;
 	const double corr = -mult * (c1 * c1 - 1.0);
-	double G = c1 * c1 * c1 * exp(corr * q[0] * q[0]);
+	double G = c1 * c1 * c1 * sxs_fit_exp(ctx, corr * q[0] * q[0]);
 	double G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q[0] * q[0]);
 
 	double xvv, xvd, xvw, xdd, xdw, xww;
@@ -134,7 +147,7 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 
 	for (int i = 0; i < ctx->qnum; i++) {
 		const double q_cur = q[i];
-		G = c1_cube * exp(corr * q_cur * q_cur);
+		G = c1_cube * sxs_fit_exp(ctx, corr * q_cur * q_cur);
 		G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q_cur * q_cur);
 
 		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
@@ -195,7 +208,7 @@ SXS_HD void sxs_fit_eval_fused(const struct sxs_fit_ctx *ctx, double sum_a0, dou
 
 	double xvv, xvd, xvw, xdd, xdw, xww;
 	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
-	double G = c1_cube * exp(corr * q[0] * q[0]);
+	double G = c1_cube * sxs_fit_exp(ctx, corr * q[0] * q[0]);
 	double G_der = G * (three_over_c1 - two_c1_mult * q[0] * q[0]);
 	double in_prev = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
 	double d1_prev = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);
@@ -211,7 +224,7 @@ SXS_HD void sxs_fit_eval_fused(const struct sxs_fit_ctx *ctx, double sum_a0, dou
 		SXS_PREFETCH_ROW(ctx, i);
 		if (i > 0) {
 			SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
-			G = c1_cube * exp(corr * q_cur * q_cur);
+			G = c1_cube * sxs_fit_exp(ctx, corr * q_cur * q_cur);
 			G_der = G * (three_over_c1 - two_c1_mult * q_cur * q_cur);
 		}
 		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;

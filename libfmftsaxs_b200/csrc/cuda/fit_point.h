@@ -24,8 +24,8 @@ SXS_HD double sxs_fit_rescale(const struct sxs_fit_ctx *ctx_unit, double peak)
 
 /* Serial form (one fit start to finish); the CUDA kernel interleaves lb_step() and the evaluation
  * across the lanes of a warp instead, see k_fit in sxs_exact.cu. */
-SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const double *a, const double *qvals, int qnum,
-                          double mult, double peak, double *score, double *c1, double *c2, int *nfg)
+SXS_HD void sxs_fit_point_ex(const double *x, long stride, long qstride, const double *a, const double *qvals, int qnum,
+                             double mult, double peak, const uint64_t *etab, double *score, double *c1, double *c2, int *nfg)
 {
 	struct sxs_fit_ctx ctx;
 	ctx.x = x;
@@ -36,6 +36,7 @@ SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const doub
 	ctx.qnum = qnum;
 	ctx.mult = mult;
 	ctx.rq = NULL; /* the serial form divides in the loop */
+	ctx.etab = etab; /* NULL on the host: libm's exp itself */
 	ctx.scale = 1.0;
 	ctx.scale = sxs_fit_rescale(&ctx, peak);
 
@@ -50,6 +51,12 @@ SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const doub
 	*c1 = st.x[1];
 	*c2 = st.x[2];
 	*nfg = st.nfgv;
+}
+
+SXS_HD void sxs_fit_point(const double *x, long stride, long qstride, const double *a, const double *qvals, int qnum,
+                          double mult, double peak, double *score, double *c1, double *c2, int *nfg)
+{
+	sxs_fit_point_ex(x, stride, qstride, a, qvals, qnum, mult, peak, NULL, score, c1, c2, nfg);
 }
 
 #endif

@@ -10,7 +10,8 @@
  *
  * K4: per objective evaluation a thread makes one pass over its 6*qnum cross terms (one exp per node,
  * sxs_fit_eval_fused); 7-13 evaluations per fit on real data, ~20 on the synthetic bench workload.  Build
- * with -DSXS_FIT_EVAL_EXACT for the reference's two-pass objective (bit-identical to it up to exp()).
+ * with -DSXS_FIT_EVAL_EXACT for the reference's two-pass objective (bit-identical to it: exp() is the reference
+ * libm's algorithm, exp_glibc.h).
  */
 #include <math.h>
 
@@ -51,6 +52,9 @@
 #define SXS_FIT_BATCH_DEN 4
 #endif
 
+/* 2^(k/128) table of the libm-faithful exp (exp_glibc.h); k_fit copies it to shared memory */
+__device__ const uint64_t d_exp_tab[SXS_EXP_TABLE_ENTRIES] = SXS_EXP_TABLE_INIT;
+
 __device__ __forceinline__ void fit_store(const struct lb_state *st, double *__restrict__ res, long long p)
 {
 	res[p * 4 + 0] = sqrt(st->f);
@@ -74,10 +78,14 @@ __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {
-	extern __shared__ double s_tab[]; /* [6*qnum] moments, [qnum] q grid, [qnum] reciprocal node spacings */
+	extern __shared__ double s_tab[]; /* [6*qnum] moments, [qnum] q grid, [qnum] reciprocal node spacings, exp table */
 	double *s_a = s_tab;
 	double *s_q = s_tab + 6 * qnum;
 	double *s_rq = s_tab + 7 * qnum;
+	uint64_t *s_etab = reinterpret_cast<uint64_t *>(s_tab + 8 * qnum);
+	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
+		s_etab[i] = d_exp_tab[i];
+	}
 	for (int i = threadIdx.x; i < 6 * qnum; i += blockDim.x) {
 		s_a[i] = a[i];
 	}
@@ -95,7 +103,7 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a;
 #endif
 	ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
-	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq;
+	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq; ctx.etab = s_etab;
 	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
 	(void)sum_a0;
 	long long p = -1;
@@ -192,7 +200,7 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	int dev = 0, sms = 148, per_sm = 4;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const size_t shm = sizeof(double) * 8 * qnum;
+	const size_t shm = sizeof(double) * 8 * qnum + sizeof(uint64_t) * SXS_EXP_TABLE_ENTRIES;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
 	if (per_sm < 1) per_sm = 1;
 	if (getenv("SXS_FIT_BLOCKS_PER_SM")) { /* tuning only */
@@ -260,7 +268,7 @@ __global__ void k_fit_eval(const double *__restrict__ cross, const double *__res
 	ctx.x = cross; /* point-major row x[q*6 + k] */
 	ctx.stride = 1;
 	ctx.qstride = 6;
-	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = NULL;
+	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = NULL; ctx.etab = d_exp_tab;
 	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
 	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);
 }
@@ -289,6 +297,30 @@ extern "C" int sxs_cuda_fit_eval(int device, const double *cross, const double *
 	SXS_CK_LAUNCH();
 	SXS_CK(cudaMemcpy(out4, d_o, sizeof(double) * 4, cudaMemcpyDeviceToHost));
 	cudaFree(d_x); cudaFree(d_a); cudaFree(d_q); cudaFree(d_o);
+	return 0;
+}
+
+__global__ void k_exp_array(const double *__restrict__ x, long long n, double *__restrict__ y)
+{
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		y[i] = sxs_exp_glibc(x[i], d_exp_tab);
+	}
+}
+
+extern "C" int sxs_cuda_exp_array(int device, const double *x, long long n, double *y)
+{
+	if (n <= 0) {
+		return 0;
+	}
+	SXS_CK(cudaSetDevice(device));
+	double *d_x = NULL, *d_y = NULL;
+	SXS_CK(cudaMalloc(&d_x, sizeof(double) * n));
+	SXS_CK(cudaMalloc(&d_y, sizeof(double) * n));
+	SXS_CK(cudaMemcpy(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+	k_exp_array<<<592, 256>>>(d_x, n, d_y);
+	SXS_CK_LAUNCH();
+	SXS_CK(cudaMemcpy(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost));
+	cudaFree(d_x); cudaFree(d_y);
 	return 0;
 }
 
@@ -368,7 +400,7 @@ __global__ void k_profile(const double2 *__restrict__ A, int qnum, int lm_n, dou
 		return;
 	}
 	const double corr = -mult * (c1 * c1 - 1.0);
-	const double G = c1 * c1 * c1 * exp(corr * q0 * q0);
+	const double G = c1 * c1 * c1 * sxs_exp_glibc(corr * q0 * q0, d_exp_tab);
 	const double2 *V = A + ((size_t)0 * qnum + q) * lm_n, *D = A + ((size_t)1 * qnum + q) * lm_n,
 	              *W = A + ((size_t)2 * qnum + q) * lm_n;
 	double acc = 0.0;

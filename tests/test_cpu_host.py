@@ -371,19 +371,31 @@ def test_no_cpu_fallback_without_device(capi):
 @pytest.fixture(scope="module")
 def fit_host(tmp_path_factory):
     out = tmp_path_factory.mktemp("fit") / "libfit_host.so"
-    subprocess.run(["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+    subprocess.run(["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared",
                     "-I" + os.path.join(REPO, "libfmftsaxs_b200", "csrc", "cuda"),
                     os.path.join(HERE, "cpu_harness", "fit_host.c"), "-lm", "-o", str(out)], check=True)
     lib = ctypes.CDLL(str(out))
 
-    def run(X, a, q, mult, peak):
+    def run(X, a, q, mult, peak, table_exp=1):
         X = np.ascontiguousarray(X)
         o = np.zeros((len(X), 4))
         lib.cpu_fit_points(refso.dptr(X), ctypes.c_int(len(X)), refso.dptr(np.ascontiguousarray(a)),
                            refso.dptr(np.ascontiguousarray(q)), ctypes.c_int(len(q)), ctypes.c_double(mult),
-                           ctypes.c_double(peak), refso.dptr(o))
+                           ctypes.c_double(peak), ctypes.c_int(table_exp), refso.dptr(o))
         return o
+    run.lib = lib
     return run
+
+
+def test_exp_restatement_equals_host_libm(fit_host):
+    """exp_glibc.h (the exp the device evaluates in the objective) against this host's libm, bit for bit, on 20 M
+    arguments: |x| < 0.02 (the fit's range), < 1, < 500, and denormal-small.  Holds on x86-64 hosts whose libm
+    runs the FMA build of exp (glibc >= 2.28 with AVX2+FMA)."""
+    flags = open("/proc/cpuinfo").read()
+    if " fma " not in flags or " avx2 " not in flags:
+        pytest.skip("host libm does not select the FMA build of exp")
+    fit_host.lib.cpu_exp_mismatches.restype = ctypes.c_long
+    assert fit_host.lib.cpu_exp_mismatches(ctypes.c_long(20_000_000)) == 0
 
 
 def test_fit_headers_bitwise_on_fixture(fit_host, G):

@@ -102,6 +102,20 @@ def test_fit_kernel_against_reference_lbfgsb(G, FC):
     assert np.mean(got[:, 3] == want[:, 3]) > 0.9
 
 
+def test_device_exp_equals_host_libm():
+    """the objective's exp() on the device (exp_glibc.h) against this host's libm (math.exp), bit for bit"""
+    import math
+    flags = open("/proc/cpuinfo").read()
+    if " fma " not in flags or " avx2 " not in flags:
+        pytest.skip("host libm does not select the FMA build of exp")
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-0.02, 0.02, 200000), rng.uniform(-1, 1, 50000), rng.uniform(-500, 500, 50000),
+                        rng.uniform(-1e-17, 1e-17, 1000), [0.0, -0.0, 5e-324, -0.01, 0.01]])
+    got = capi.cuda_exp(x)
+    want = np.array([math.exp(v) for v in x])
+    assert np.array_equal(got.view(np.int64), want.view(np.int64))
+
+
 def test_cross_terms_z40(G, FC):
     """K2+K3 stage output vs the numpy restatement driven by reference tables"""
     q, L = G["qvals"], int(G["L"])
