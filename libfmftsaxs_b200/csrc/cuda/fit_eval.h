@@ -156,7 +156,12 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 		const double in_der_c1 = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);
 		const double in_der_c2 = xvw - G * xdw + 2.0 * c2 * xww;
 
-		double buf = 1.0 / (q_cur - q_prev);
+		/* 1 / (q_i - q_{i-1}): from the table when there is one (the same IEEE quotient, computed once per block) */
+#if defined(__CUDA_ARCH__)
+		double buf = ctx->rq[i];
+#else
+		double buf = ctx->rq ? ctx->rq[i] : 1.0 / (q_cur - q_prev);
+#endif
 		const double tan = (in - in_prev) * buf;
 		const double tan_c1_der = (in_der_c1 - in_der_c1_prev) * buf;
 		const double tan_c2_der = (in_der_c2 - in_der_c2_prev) * buf;

@@ -5,7 +5,9 @@
 #define SXS_FIT_POINT_H
 
 #include "fit_eval.h"
-#include "lbfgsb_n2m3.h"
+#ifdef SXS_FIT_GENERIC_LBFGSB
+#include "lbfgsb_n2m3.h" /* the memory-resident restatement with the vendored code's loop structure (host comparisons) */
+#endif
 
 #define SXS_C1_LOWER 0.96
 #define SXS_C1_UPPER 1.04
@@ -13,6 +15,14 @@
 #define SXS_C2_UPPER 4.00
 #define SXS_C1_DEFAULT 1.0
 #define SXS_C2_DEFAULT 0.0
+#define LQ_L1 SXS_C1_LOWER
+#define LQ_U1 SXS_C1_UPPER
+#define LQ_L2 SXS_C2_LOWER
+#define LQ_U2 SXS_C2_UPPER
+#include "lbfgsb_lean.h"
+/* factr * epsmch (lbfgsb.c mainlb) and pgtol, src/min_saxs.c:224-225 */
+#define SXS_FIT_TOL (1e+7 * LQ_EPSMCH)
+#define SXS_FIT_PGTOL 1e-5
 
 /* peak / I(0) of sxs_fit_params, in the reference's summation order (src/min_saxs.c:170-179) */
 SXS_HD double sxs_fit_rescale(const struct sxs_fit_ctx *ctx_unit, double peak)
@@ -40,13 +50,21 @@ SXS_HD void sxs_fit_point_ex(const double *x, long stride, long qstride, const d
 	ctx.scale = 1.0;
 	ctx.scale = sxs_fit_rescale(&ctx, peak);
 
-	struct lb_state st;
-	lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
 	const double sum_a0 = sxs_fit_sum_a0(a, qnum);
 	(void)sum_a0;
+#ifdef SXS_FIT_GENERIC_LBFGSB
+	struct lb_state st;
+	lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
 	while (lb_step(&st, 1e-5) == LB_NEED_EVAL) {
 		SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 	}
+#else
+	struct lq_state st;
+	lq_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT);
+	while (lq_step(&st, SXS_FIT_PGTOL, SXS_FIT_TOL) == LQ_NEED_EVAL) {
+		SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+	}
+#endif
 	*score = sqrt(st.f);
 	*c1 = st.x[1];
 	*c2 = st.x[2];

@@ -21,9 +21,12 @@
 #ifndef SXS_X_TILED
 #define SXS_ROWMAJOR_VEC 1
 #endif
-#ifndef SXS_FIT_EVAL_EXACT
-#define SXS_FIT_EVAL_FUSED 1   /* [B200] 1.12 M fits: 66.8 ms two-pass, 52.5 ms one-pass */
-#define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory: 51.8 ms */
+/* The objective is the reference's two-pass form (sxs_fit_eval), bit-identical to it.  -DSXS_FIT_EVAL_FUSED builds the
+ * one-pass form of round 1 (algebraically equal, 27 % cheaper per evaluation): on the real 4G9S list it leaves 17 of
+ * 1131 / 45 of 70 000 rows beyond 1e-6 in c2 against 3 / 10 for the two-pass form (gpurun_out/r2a_pytest_*.txt), so
+ * it is not what ships. */
+#ifdef SXS_FIT_EVAL_FUSED
+#define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory */
 #endif
 #ifndef SXS_XLD
 #define SXS_XLD __ldcs         /* cross-term rows are streamed (evict-first): 49.5 ms */
@@ -38,10 +41,7 @@
 #define SXS_FIT_THREADS 256
 #endif
 #ifndef SXS_FIT_MINBLOCKS
-#define SXS_FIT_MINBLOCKS 3
-#endif
-#ifndef SXS_FIT_WARPSYNC
-#define SXS_FIT_BLOCKSYNC 1 /* [B200] 1.12 M fits: 88 ms with warp-level rounds, 67 ms with block-level rounds */
+#define SXS_FIT_MINBLOCKS 1
 #endif
 
 /* part B of the optimiser runs when NUM/DEN of the block's running fits wait for it (or none can evaluate) */
@@ -55,7 +55,7 @@
 /* 2^(k/128) table of the libm-faithful exp (exp_glibc.h); k_fit copies it to shared memory */
 __device__ const uint64_t d_exp_tab[SXS_EXP_TABLE_ENTRIES] = SXS_EXP_TABLE_INIT;
 
-__device__ __forceinline__ void fit_store(const struct lb_state *st, double *__restrict__ res, long long p)
+__device__ __forceinline__ void fit_store(const struct lq_state *st, double *__restrict__ res, long long p)
 {
 	res[p * 4 + 0] = sqrt(st->f);
 	res[p * 4 + 1] = st->x[1];
@@ -63,17 +63,21 @@ __device__ __forceinline__ void fit_store(const struct lb_state *st, double *__r
 	res[p * 4 + 3] = (double)st->nfgv;
 }
 
-/* K4.  X comes in tiles of 32 points (sxs_x_index): a warp takes a whole tile, lane = point, and reads every term
- * of every node with one coalesced 256-byte load; a lane whose fit has ended idles until the warp's slowest fit is
- * done, then the warp takes the next tile from the ticket counter.  [B200] 1.12 M fits: 47.5 ms with point-major
- * rows and per-lane refill, 46.0 ms tiled (K3's stores become coalesced too: 35.4 -> 34.5 ms).  -DSXS_X_ROWMAJOR
- * builds the point-major form: contiguous rows X[p*6*qnum + q*6 + k], 16-byte loads, per-lane refill.
+/* K4.  X comes in tiles of 32 points (sxs_x_index): a warp takes a whole tile, lane = point, and reads every term of
+ * every node with one coalesced 256-byte load; a lane whose fit has ended idles until the warp's slowest fit is done,
+ * then the warp takes the next tile from the ticket counter.
  *
- * Every lane owns one fit at a time and runs the reverse-communication optimiser (lb_step_a / lb_step_b) until it
- * asks for the objective; then all warps of the block evaluate the objective together.  The optimiser logic is
- * branchy and diverges between lanes, the objective (one pass over q with one exp per node, most of the
- * arithmetic) is executed convergently (evaluations per fit range from 2 to ~60).
- * Variants measured and rejected are logged in profiles/r1_k4_notes.md. */
+ * Every lane owns one fit and runs the reverse-communication optimiser (lbfgsb_lean.h: all of its state in registers)
+ * until it asks for the objective; the objective — two passes over the q nodes like the reference, the bulk of the
+ * arithmetic — is evaluated convergently by the lanes that want it (evaluations per fit range from 2 to ~60).
+ * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) is run when at least NUM/DEN of the
+ * round's waiting fits wait for it, so that it executes with most lanes active.
+ *
+ * Rounds are per warp by default; -DSXS_FIT_BLOCK_ROUNDS synchronises them over the block (round 1's form, when the
+ * optimiser was 3x the code and shared instruction fetch mattered).  Tuning log: profiles/r2_k4_notes.md. */
+#ifndef SXS_X_TILED
+#error "k_fit reads the tiled cross-term layout"
+#endif
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
@@ -95,13 +99,9 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	}
 	__syncthreads();
 
-	struct lb_state st;
+	struct lq_state st;
 	struct sxs_fit_ctx ctx;
-#ifdef SXS_X_TILED
 	ctx.stride = 32; ctx.qstride = 6 * 32; ctx.a = s_a;
-#else
-	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a;
-#endif
 	ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
 	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq; ctx.etab = s_etab;
 	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
@@ -115,30 +115,30 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	for (;;) {
 		/* (1) line-search turn (part A of the optimiser, short) for every lane that has a fresh f, g */
 		if (mode == EVALUATED) {
-			const int r = lb_step_a(&st);
-			mode = (r == LB_NEED_EVAL) ? WANT_EVAL : (r == LB_NEED_B) ? WANT_B : FREE;
-			if (r == LB_DONE) {
+			const int r = lq_step_a(&st);
+			mode = (r == LQ_NEED_EVAL) ? WANT_EVAL : (r == LQ_NEED_B) ? WANT_B : FREE;
+			if (r == LQ_DONE) {
 				fit_store(&st, res, p);
 			}
 		}
-		/* (2) iteration boundary (part B: BFGS update, Cauchy point, subspace step; ~17x the instructions of
-		 * an evaluation) is run by the whole block at once, and only when enough of its lanes wait for it:
-		 * a lane that has finished its line search idles through a few evaluation rounds instead of
-		 * dragging its warp through part B with a third of the lanes active. */
+		/* (2) iteration boundary, when enough of the round's fits wait for it */
+#ifdef SXS_FIT_BLOCK_ROUNDS
 		const int n_b = __syncthreads_count(mode == WANT_B);
 		const int n_e = __syncthreads_count(mode == WANT_EVAL);
+#else
+		const int n_b = __popc(__ballot_sync(0xffffffffu, mode == WANT_B));
+		const int n_e = __popc(__ballot_sync(0xffffffffu, mode == WANT_EVAL));
+#endif
 		if (n_b > 0 && (n_e == 0 || n_b * SXS_FIT_BATCH_DEN >= (n_b + n_e) * SXS_FIT_BATCH_NUM)) {
 			if (mode == WANT_B) {
-				const int r = lb_step_b(&st, 1e-5);
-				mode = (r == LB_NEED_EVAL) ? WANT_EVAL : FREE;
-				if (r == LB_DONE) {
+				const int r = lq_step_b(&st, SXS_FIT_PGTOL, SXS_FIT_TOL);
+				mode = (r == LQ_NEED_EVAL) ? WANT_EVAL : FREE;
+				if (r == LQ_DONE) {
 					fit_store(&st, res, p);
 				}
 			}
 		}
-		/* (3) free lanes take the next point from the ticket counter */
-#ifdef SXS_X_TILED
-		/* a warp takes a whole tile of 32 points when all its lanes are free: lane = point inside the tile */
+		/* (3) a warp takes a whole tile of 32 points when all its lanes are free: lane = point inside the tile */
 		const bool warp_free = __all_sync(0xffffffffu, mode == FREE);
 		if (warp_free && !drained) {
 			unsigned long long tile = 0;
@@ -152,33 +152,31 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 			}
 			if (p < npts) {
 				ctx.x = X + sxs_x_index(p, qnum, 0, 0);
-#else
-		if (mode == FREE && !drained) {
-			p = (long long)atomicAdd(ticket, 1ull);
-			if (p < npts) {
-				ctx.x = X + (size_t)p * 6 * qnum;
-#endif
 				ctx.scale = 1.0;
 				if (rescale) {
 					ctx.scale = sxs_fit_rescale(&ctx, peak);
 				}
-				lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
-				const int r = lb_step_a(&st); /* projects the start into the box and asks for f, g there */
-				mode = (r == LB_NEED_EVAL) ? WANT_EVAL : (r == LB_NEED_B) ? WANT_B : FREE;
-				if (r == LB_DONE) {
+				lq_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT);
+				const int r = lq_step_a(&st); /* projects the start into the box and asks for f, g there */
+				mode = (r == LQ_NEED_EVAL) ? WANT_EVAL : (r == LQ_NEED_B) ? WANT_B : FREE;
+				if (r == LQ_DONE) {
 					fit_store(&st, res, p);
 				}
-			} else {
-#ifndef SXS_X_TILED
-				drained = true;
-#endif
 			}
 		}
-		/* (4) all warps of the block enter the evaluation together: they share the instruction stream, which is
-		 * what the instruction cache of the SM needs (5 700 SASS instructions in total) */
+		/* (4) the objective */
+#ifdef SXS_FIT_BLOCK_ROUNDS
 		if (!__syncthreads_or(mode != FREE)) {
 			break;
 		}
+#else
+		if (!__any_sync(0xffffffffu, mode != FREE)) {
+			if (drained) {
+				break;
+			}
+			continue;
+		}
+#endif
 		if (mode == WANT_EVAL) {
 			SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 			mode = EVALUATED;
@@ -268,7 +266,11 @@ __global__ void k_fit_eval(const double *__restrict__ cross, const double *__res
 	ctx.x = cross; /* point-major row x[q*6 + k] */
 	ctx.stride = 1;
 	ctx.qstride = 6;
-	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = NULL; ctx.etab = d_exp_tab;
+	double rq[SXS_FIT_MAXQ];
+	for (int i = 0; i < qnum; i++) {
+		rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
+	}
+	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = rq; ctx.etab = d_exp_tab;
 	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
 	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);
 }

@@ -100,9 +100,65 @@ struct shard_job {
 	const long long *idx64;
 	long long nout;
 	double *scores, *c1, *c2;
+	long long cell5; /* grid points per z step: index / cell5 = z digit */
+	int compact;     /* several devices: this shard extracts its own rows first (see shard_main) */
+	long long rows;  /* rows this shard scored */
 	int rc;
 	char err[512]; /* the CUDA layer's message of this thread (its error buffer is thread-local) */
 };
+
+/* With several devices every shard first extracts the rows of its own z range — one pass over the index list on
+ * its own host thread — and hands the device that compact list only: uploads, the key sort and the scatter then
+ * scale with the shard, not with the whole list (the reference's MPI ranks do the same filtering while reading the
+ * Euler file, tools/correlate.c:169-251).  Results go back to the caller's arrays at the rows' input positions;
+ * rows outside every range are never written. */
+static int shard_score_compact(struct shard_job *j)
+{
+	long long n = 0;
+	for (long long i = 0; i < j->nout; i++) {
+		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
+		n += v >= 0 && v / j->cell5 >= j->z_lo && v / j->cell5 < j->z_hi;
+	}
+	j->rows = n;
+	if (n == 0) {
+		return 0;
+	}
+	long long *pos = (long long *)malloc(sizeof(long long) * (size_t)n);
+	void *sub = malloc((j->idx32 != NULL ? sizeof(int) : sizeof(long long)) * (size_t)n);
+	double *out = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+	if (pos == NULL || sub == NULL || out == NULL) {
+		free(pos); free(sub); free(out);
+		snprintf(j->err, sizeof(j->err), "out of host memory for a shard of %lld rows", n);
+		return -1;
+	}
+	long long k = 0;
+	for (long long i = 0; i < j->nout; i++) {
+		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
+		if (v >= 0 && v / j->cell5 >= j->z_lo && v / j->cell5 < j->z_hi) {
+			pos[k] = i;
+			if (j->idx32 != NULL) {
+				((int *)sub)[k] = j->idx32[i];
+			} else {
+				((long long *)sub)[k] = v;
+			}
+			out[k] = j->scores[i]; out[n + k] = j->c1[i]; out[2 * n + k] = j->c2[i];
+			k++;
+		}
+	}
+	int rc;
+	if (j->idx32 != NULL) {
+		rc = sxs_cuda_plan_score_i32(j->plan, (const int *)sub, n, j->z_lo, j->z_hi, out, out + n, out + 2 * n);
+	} else {
+		rc = sxs_cuda_plan_score_i64(j->plan, (const long long *)sub, n, j->z_lo, j->z_hi, out, out + n, out + 2 * n);
+	}
+	if (rc == 0) {
+		for (k = 0; k < n; k++) {
+			j->scores[pos[k]] = out[k]; j->c1[pos[k]] = out[n + k]; j->c2[pos[k]] = out[2 * n + k];
+		}
+	}
+	free(pos); free(sub); free(out);
+	return rc;
+}
 
 static void *shard_main(void *arg)
 {
@@ -111,13 +167,15 @@ static void *shard_main(void *arg)
 	if (j->rc == 0) j->rc = sxs_cuda_plan_set_experiment(j->plan, j->a, j->mult, j->peak);
 	if (j->rc == 0) j->rc = sxs_cuda_plan_set_translations(j->plan, j->bessel, j->znum);
 	if (j->rc == 0) {
-		if (j->idx32 != NULL) {
+		if (j->compact) {
+			j->rc = shard_score_compact(j);
+		} else if (j->idx32 != NULL) {
 			j->rc = sxs_cuda_plan_score_i32(j->plan, j->idx32, j->nout, j->z_lo, j->z_hi, j->scores, j->c1, j->c2);
 		} else {
 			j->rc = sxs_cuda_plan_score_i64(j->plan, j->idx64, j->nout, j->z_lo, j->z_hi, j->scores, j->c1, j->c2);
 		}
 	}
-	if (j->rc != 0) {
+	if (j->rc != 0 && j->err[0] == 0) {
 		snprintf(j->err, sizeof(j->err), "%s", sxs_cuda_last_error());
 	}
 	return NULL;
@@ -208,6 +266,10 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 		j->znum = znum; j->z_lo = z_lo; j->z_hi = z_next;
 		j->idx32 = idx32; j->idx64 = idx64; j->nout = nout;
 		j->scores = scores; j->c1 = c1; j->c2 = c2;
+		j->cell5 = cell5;
+	}
+	for (int k = 0; k < njobs; k++) {
+		jobs[k].compact = njobs > 1;
 	}
 	if (njobs == 1) {
 		shard_main(&jobs[0]);

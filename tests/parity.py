@@ -52,22 +52,30 @@ def fmt(tag, sm):
 
 
 # ---- the acceptance rule of the -m gpu parity tests -------------------------------------------------------------
-# chi: every row within TOL (the minimum is flat, chi does not feel where on the valley floor the minimiser stops).
-# c1, c2: every row within TOL except at most OUTLIER_RATE of the rows — the rate at which the reference disagrees
-#         with its own FMA build on the real 4G9S list (1 of 1131 rows; tests/golden/make_golden_bench.py stores that
-#         build's answers next to the reference's) — and no outlier further than OUTLIER_CAP.
+# chi: every row within TOL (the minimum is flat: chi does not feel where on the valley floor the minimiser stops).
+# c1, c2: every row within TOL except a counted few.  K4 itself is bit-identical to the reference's L-BFGS-B on equal
+#         cross terms (test_fit_kernel_against_reference_lbfgsb), so every deviation comes from rounding-level
+#         differences (~1e-13) of the cross terms, which the mid-convergence stop of the minimiser amplifies on single
+#         rows.  The reference does the same to ITSELF: its own sources built with FMA contraction
+#         (oracle/_ref/libsxsref_fma.so; answers stored in the fixtures as sens_*) leave 9 of the 70 000 real rows and
+#         1 of the 1131 six-z rows beyond 1e-6 in c2 (max 2.1e-6).  Allowed here: max(OUTLIER_RATE * rows,
+#         3 + 2 * the reference's own count), none further than OUTLIER_CAP.
 OUTLIER_RATE = 1e-3
-OUTLIER_CAP = 1e-2
+OUTLIER_CAP = 1e-4
 
 
 def check(tag, got, want, rate=OUTLIER_RATE, cap=OUTLIER_CAP, sens=None):
     sm = summary(got, want)
     print(fmt(tag, sm))
+    own = 0
     if sens is not None:
-        print(fmt(tag + " [reference vs its own FMA build]", summary(sens, want)))
+        ss = summary(sens, want)
+        own = ss["rows_over_tol"]
+        print(fmt(tag + " [reference vs its own FMA build]", ss))
     if sm["rows"] == 0:
         return sm
     assert sm["max_rel_chi"] < TOL, tag
-    assert sm["rows_over_tol"] <= int(rate * sm["rows"]), "%s: %d rows beyond %g" % (tag, sm["rows_over_tol"], TOL)
+    allowed = max(int(rate * sm["rows"]), (3 + 2 * own) if sens is not None else 0)
+    assert sm["rows_over_tol"] <= allowed, "%s: %d rows beyond %g (allowed %d)" % (tag, sm["rows_over_tol"], TOL, allowed)
     assert max(sm["max_rel_c1"], sm["max_rel_c2"]) < cap, tag
     return sm

@@ -27,7 +27,8 @@ def test_real_list_70k_rows_against_reference():
     R = np.load(os.path.join(GOLD, "golden_real70k.npz"))
     q, L = G["qvals"], int(G["L"])
     s, c1, c2 = capi.scores(R["index"], G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, R["zvals"], L)
-    parity.check("real list, 70 000 rows", (s, c1, c2), (R["scores"], R["c1"], R["c2"]))
+    parity.check("real list, 70 000 rows", (s, c1, c2), (R["scores"], R["c1"], R["c2"]),
+                 sens=(R["sens_scores"], R["sens_c1"], R["sens_c2"]))
     # text-level contract of the output file: three decimals
     assert np.mean(np.round(s, 3) == np.round(R["scores"], 3)) > 0.999
 
