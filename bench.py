@@ -221,8 +221,10 @@ def run_product(args):
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier for the e2e leg (no spinning kernels on the GPUs)
 
     def native_cross(idx, coefA, coefB, q, zv, L):
         pl = capi.Plan(L, q, device=local)
@@ -233,9 +235,19 @@ def run_product(args):
         pl.close()
         return X
 
-    w = build_inputs(capi.expand, capi.opt_params, native_cross, rank, args.nrot, args.nz)
+    strong = args.scaling == "strong" and world > 1
+    w = build_inputs(capi.expand, capi.opt_params, native_cross, 0 if strong else rank, args.nrot, args.nz)
     L, q, zvals, idx = w["L"], w["qvals"], w["zvals"], w["index"]
+    full_idx = idx
+    gsh = None
+    if strong:
+        # ONE list over the ranks: every rank filters the rows of its own z range (the reference's MPI scheme,
+        # tools/correlate.c:140-147) and the score table is gathered into input order inside the timed step
+        from libfmftsaxs_b200 import dist as sd
+        gsh = sd.RowShardGather(full_idx, L, len(zvals), world, rank, device=dev)
+        idx = np.ascontiguousarray(full_idx[gsh.my_rows])
     n = len(idx)
+    n_job = len(full_idx) if strong else world * n   # poses the whole job scores per step
     plan = capi.Plan(L, q, device=local)
     plan.set_molecules(w["coefA"], w["coefB"])
     plan.set_experiment(w["a"], w["scal"][1], w["scal"][2])
@@ -243,13 +255,15 @@ def run_product(args):
 
     is64 = idx.dtype == np.int64
     d_idx = torch.from_numpy(idx).to(dev)
-    d_out = torch.zeros((3, n), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * 3, n), dtype=torch.float64, device=dev) if world > 1 else None
+    d_out = gsh.local if strong else torch.zeros((3, n), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * 3, n), dtype=torch.float64, device=dev) if (world > 1 and not strong) else None
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         plan.score_device(d_idx.data_ptr(), n, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), stream, i64=is64)
-        if world > 1:
+        if strong:
+            gsh.gather()
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, d_out)
 
     def barrier():
@@ -285,11 +299,18 @@ def run_product(args):
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    value = world * n * args.steps / (ms * 1e-3)
+    value = n_job * args.steps / (ms * 1e-3)
 
     # ---- end to end through the reference-shaped API with host buffers ----
-    h_idx = torch.from_numpy(idx).pin_memory()
-    h_out = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    # strong scaling: rank 0 alone calls the API on the WHOLE list with every GPU of the job named in SXS_CUDA_DEVICES
+    # (one host thread per device inside the library: the drop-in replacement of `mpirun -np N correlate`); the other
+    # ranks wait at the barrier.  Weak scaling: every rank calls the API on its own list.
+    e2e_idx = full_idx if strong else idx
+    e2e_n = len(e2e_idx)
+    if strong:
+        os.environ["SXS_CUDA_DEVICES"] = ",".join(str(d) for d in range(world))
+    h_idx = torch.from_numpy(e2e_idx).pin_memory()
+    h_out = [torch.zeros(e2e_n, dtype=torch.float64).pin_memory() for _ in range(3)]
     import ctypes as C
     lib = capi.lib()
     dp = C.POINTER(C.c_double)
@@ -299,31 +320,46 @@ def run_product(args):
         args_tail = (capi.dptr(cA), capi.dptr(cB), capi.dptr(a_), capi.dptr(sc_), capi.dptr(q_), C.c_int(len(q_)),
                      capi.dptr(z_), C.c_int(len(z_)), C.c_int(L), C.c_int(1))
         o = [C.cast(t.data_ptr(), dp) for t in h_out]
+        if strong and rank != 0:
+            return 0.0
         if is64:
-            lib.sxs_flat_scores64(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_longlong)), C.c_longlong(n), *args_tail)
+            lib.sxs_flat_scores64(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_longlong)), C.c_longlong(e2e_n), *args_tail)
         else:
-            lib.sxs_flat_scores(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_int)), C.c_int(n), *args_tail)
+            lib.sxs_flat_scores(o[0], o[1], o[2], C.cast(h_idx.data_ptr(), C.POINTER(C.c_int)), C.c_int(e2e_n), *args_tail)
         return float(h_out[0][0])
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
-    barrier()
+    host_barrier()
     te = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    barrier()
+    host_barrier()
     e2e_s = time.perf_counter() - te
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_value = world * n * e2e_steps / e2e_s
+    e2e_value = n_job * e2e_steps / e2e_s
     N = 2 * L + 1
-    h2d = idx.nbytes + cA.nbytes + cB.nbytes + a_.nbytes + len(z_) * len(q_) * N * 8
-    d2h = n * (3 * 8 + 4)
+    tables = cA.nbytes + cB.nbytes + a_.nbytes + len(z_) * len(q_) * N * 8
+    if strong:
+        h2d = full_idx.nbytes + world * tables      # every device gets the tables, each its own rows
+        d2h = len(full_idx) * (3 * 8 + 4)
+    else:
+        h2d = idx.nbytes + tables
+        d2h = n * (3 * 8 + 4)
 
-    # parity spot check of what was just timed: resident path == host path (same kernels), finite, in the box
-    same = bool(np.array_equal(d_out[0].cpu().numpy(), h_out[0].numpy()))
+    # parity spot check of what was just timed: resident path == host path (same kernels)
+    if strong:
+        same = bool(rank != 0 or np.array_equal(gsh.table[0, :len(full_idx)].cpu().numpy(), h_out[0].numpy()))
+    else:
+        same = bool(np.array_equal(d_out[0].cpu().numpy(), h_out[0].numpy()))
 
     line = None
     if rank == 0:
@@ -361,16 +397,20 @@ def run_product(args):
         roofline, roofline2 = (r_fit, r_cross) if fit_ms >= cross_ms else (r_cross, r_fit)
         cpu, parity_line = cpu_baseline(w, args, d_out)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "poses_per_gpu": int(n), "distinct_grid_points": int(stats["points"]),
+                "config": {"workload": WORKLOAD, "poses_per_gpu": int(n), "poses_per_step_whole_job": int(n_job),
+                           "list": ("one list of %d poses split over %d GPUs by z range, score table gathered into input order "
+                                    "inside the step" % (len(full_idx), world)) if strong else "one list per GPU",
+                           "distinct_grid_points": int(stats["points"]),
                            "L": L, "qnum": Q, "z_steps": int(len(zvals)), "rec_atoms": len(w["rec"]["res"]),
                            "lig_atoms": len(w["lig"]["res"]),
                            "l2_policy": "inputs larger than L2 (rotated tables %.0f MB + translated slabs %.1f GB per step)"
                                         % (2 * (L + 1) * Q * 3 * ML * N * 16 / 1e6, stats["slabs"] * Q * 3 * ML * N * 16 / 1e9)},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_steps, "api": "sxs_compute_saxs_scores (flat adapter), pinned host buffers"},
+                        "steps": e2e_steps, "api": "sxs_compute_saxs_scores (flat adapter), pinned host buffers"
+                        + (", ONE call on rank 0 driving all %d GPUs (SXS_CUDA_DEVICES)" % world if strong else "")},
                 "gpu_launches": int(stats["launches"] * args.steps),
                 "kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
                 "fit_evaluations": {"mean": nfg_mean, "p50": int(np.searchsorted(np.cumsum(hist), 0.5 * hist.sum())),
@@ -473,6 +513,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, help="pose-list/molecule configuration of libfmftsaxs_b200.workload.CONFIGS "
                     "(default: BASELINE config 3; config 4 is a separate measurement, see profiles/)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = ONE pose list of the workload's size split over the GPUs (default; what correlate "
+                         "under MPI does); weak = every GPU scores its own list of that size")
     ap.add_argument("--nrot", type=int, default=None, help="override rotations per z (default 70000)")
     ap.add_argument("--nz", type=int, default=None, help="override number of z steps (default 64)")
     ap.add_argument("--cpu-slabs", type=int, default=3)

@@ -35,6 +35,7 @@ struct sxs_fit_ctx {
 	double mult;          /* (4pi/3)^(3/2) rm^2 / (16 pi), src/min_saxs.c:121 */
 	double scale;         /* peak / I(0) rescale, src/min_saxs.c:170-179 */
 	const double *rq;     /* optional table rq[i] = 1/(q_i - q_{i-1}), q_{-1} = -1 (same IEEE quotient as in the loop) */
+	const double *dq;     /* optional table dq[i] = q_i - q_{i-1}, q_{-1} = -1 (the difference the loops form) */
 	const uint64_t *etab; /* 2^(k/128) table of exp_glibc.h; NULL on the host = call libm's exp itself */
 };
 
@@ -89,107 +90,160 @@ enum { SXS_VV = 0, SXS_VD, SXS_VW, SXS_DD, SXS_DW, SXS_WW };
 #define SXS_PREFETCH_ROW(ctx, i) do { } while (0)
 #endif
 
+/* ---- the objective node by node ------------------------------------------------------------------------------
+ * Both passes of the reference walk the q nodes with a handful of running values.  They are written here as
+ * "begin at node 0" + "advance by one node" steps on the six scaled cross terms of that node, so that the serial form
+ * below (pointer + strides) and the kernel's streamed form (terms arriving through a shared-memory ring) execute the
+ * same expressions in the same order. */
+struct sxs_six {
+	double vv, vd, vw, dd, dw, ww;
+};
+
+/* pass 1, src/min_saxs.c:261-319 */
+struct sxs_scale_run {
+	double corr, c1_cube, c2;
+	double in_prev, q_prev, up, down;
+};
+
+SXS_HD void sxs_scale_begin(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, double c1, double c2,
+                            const struct sxs_six *x0)
+{
+	const double *q = ctx->qvals;
+	r->corr = -ctx->mult * (c1 * c1 - 1.0);
+	const double G = c1 * c1 * c1 * sxs_fit_exp(ctx, r->corr * q[0] * q[0]);
+	r->in_prev = x0->vv - G * x0->vd + c2 * x0->vw + G * G * x0->dd - G * c2 * x0->dw + c2 * c2 * x0->ww;
+	r->c1_cube = c1 * c1 * c1;
+	r->c2 = c2;
+	r->q_prev = -1.0;
+	r->up = 0.0;
+	r->down = 0.0;
+}
+
+SXS_HD void sxs_scale_node(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+{
+	const double *a = ctx->a;
+	const double c2 = r->c2;
+	const double q_cur = ctx->qvals[i];
+	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
+	const double in = x->vv - G * x->vd + c2 * x->vw + G * G * x->dd - G * c2 * x->dw + c2 * c2 * x->ww;
+#if defined(__CUDA_ARCH__)
+	const double tan = (in - r->in_prev) / ctx->dq[i];
+#else
+	const double tan = (in - r->in_prev) / (ctx->dq ? ctx->dq[i] : q_cur - r->q_prev);
+#endif
+	const double buf = in - tan * q_cur;
+
+	r->up += buf * a[i * 6 + 1] + tan * a[i * 6 + 2];
+	r->down += buf * buf * a[i * 6 + 3] + 2.0 * tan * buf * a[i * 6 + 4] + tan * tan * a[i * 6 + 5];
+
+	r->in_prev = in;
+	r->q_prev = q_cur;
+}
+
+/* pass 2, src/min_saxs.c:3-105 with k frozen */
+struct sxs_grad_run {
+	double corr, c1, c1_cube, c2, k;
+	double three_over_c1, two_c1_mult; /* the node-independent factors of dG/dc1 = G (3/c1 - 2 c1 mult q^2) */
+	double in_prev, in_der_c1_prev, in_der_c2_prev, q_prev;
+	double grad0, grad1, score;
+};
+
+SXS_HD void sxs_grad_begin(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, double c1, double c2, double k,
+                           const struct sxs_six *x0)
+{
+	const double *q = ctx->qvals;
+	const double mult = ctx->mult;
+	r->corr = -mult * (c1 * c1 - 1.0);
+	const double G = c1 * c1 * c1 * sxs_fit_exp(ctx, r->corr * q[0] * q[0]);
+	r->three_over_c1 = 3.0 / c1;
+	r->two_c1_mult = 2.0 * c1 * mult;
+	const double G_der = G * (r->three_over_c1 - r->two_c1_mult * q[0] * q[0]);
+	r->in_prev = x0->vv - G * x0->vd + c2 * x0->vw + G * G * x0->dd - G * c2 * x0->dw + c2 * c2 * x0->ww;
+	r->in_der_c1_prev = -G_der * x0->vd + 2.0 * G * G_der * x0->dd - G_der * c2 * x0->dw;
+	r->in_der_c2_prev = x0->vw - G * x0->dw + 2.0 * c2 * x0->ww;
+	r->c1 = c1;
+	r->c1_cube = c1 * c1 * c1;
+	r->c2 = c2;
+	r->k = k;
+	r->q_prev = -1.0;
+	r->grad0 = 0.0;
+	r->grad1 = 0.0;
+	r->score = 0.0;
+}
+
+SXS_HD void sxs_grad_node(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+{
+	const double *a = ctx->a;
+	const double c2 = r->c2, k = r->k;
+	const double q_cur = ctx->qvals[i];
+	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
+	const double G_der = G * (r->three_over_c1 - r->two_c1_mult * q_cur * q_cur);
+
+	const double in = x->vv - G * x->vd + c2 * x->vw + G * G * x->dd - G * c2 * x->dw + c2 * c2 * x->ww;
+	const double in_der_c1 = G_der * (-x->vd + 2.0 * G * x->dd - c2 * x->dw);
+	const double in_der_c2 = x->vw - G * x->dw + 2.0 * c2 * x->ww;
+
+	/* 1 / (q_i - q_{i-1}): from the table when there is one (the same IEEE quotient, computed once per block) */
+#if defined(__CUDA_ARCH__)
+	double buf = ctx->rq[i];
+#else
+	double buf = ctx->rq ? ctx->rq[i] : 1.0 / (q_cur - r->q_prev);
+#endif
+	const double tan = (in - r->in_prev) * buf;
+	const double tan_c1_der = (in_der_c1 - r->in_der_c1_prev) * buf;
+	const double tan_c2_der = (in_der_c2 - r->in_der_c2_prev) * buf;
+
+	const double a1 = a[i * 6 + 1], a2 = a[i * 6 + 2], a3 = a[i * 6 + 3], a4 = a[i * 6 + 4], a5 = a[i * 6 + 5];
+
+	r->grad0 += 2.0 * k * (-(in_der_c1 - tan_c1_der * q_cur) * a1 - tan_c1_der * a2 +
+	                       k * ((in - tan * q_cur) * (in_der_c1 - tan_c1_der * q_cur) * a3 +
+	                            (in * tan_c1_der + in_der_c1 * tan - 2.0 * tan * tan_c1_der * q_cur) * a4 +
+	                            tan * tan_c1_der * a5));
+
+	r->grad1 += 2.0 * k * (-(in_der_c2 - tan_c2_der * q_cur) * a1 - tan_c2_der * a2 +
+	                       k * ((in - tan * q_cur) * (in_der_c2 - tan_c2_der * q_cur) * a3 +
+	                            (in * tan_c2_der + in_der_c2 * tan - 2.0 * tan * tan_c2_der * q_cur) * a4 +
+	                            tan * tan_c2_der * a5));
+
+	buf = in - tan * q_cur;
+	r->score += a[i * 6] + k * (-2.0 * buf * a1 - 2.0 * tan * a2 +
+	                            k * (buf * buf * a3 + 2.0 * buf * tan * a4 + tan * tan * a5));
+
+	r->in_prev = in;
+	r->in_der_c1_prev = in_der_c1;
+	r->in_der_c2_prev = in_der_c2;
+	r->q_prev = q_cur;
+}
+
 /* src/min_saxs.c:261-319 */
 SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, double c2)
 {
-	const double *a = ctx->a;
-	const double *q = ctx->qvals;
-	const double mult = ctx->mult;
-	const double corr = -mult * (c1 * c1 - 1.0);
-	double G = c1 * c1 * c1 * sxs_fit_exp(ctx, corr * q[0] * q[0]);
-
-	double xvv, xvd, xvw, xdd, xdw, xww;
-	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
-	double in_prev = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
-	const double c1_cube = c1 * c1 * c1;
-	double q_prev = -1.0;
-	double up = 0.0, down = 0.0;
-
+	struct sxs_six x;
+	struct sxs_scale_run r;
+	SXS_LOAD6(ctx, 0, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+	sxs_scale_begin(&r, ctx, c1, c2, &x);
 	for (int i = 0; i < ctx->qnum; i++) {
-		const double q_cur = q[i];
-		G = c1_cube * sxs_fit_exp(ctx, corr * q_cur * q_cur);
-		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
-		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
-		const double tan = (in - in_prev) / (q_cur - q_prev);
-		const double buf = in - tan * q_cur;
-
-		up += buf * a[i * 6 + 1] + tan * a[i * 6 + 2];
-		down += buf * buf * a[i * 6 + 3] + 2.0 * tan * buf * a[i * 6 + 4] + tan * tan * a[i * 6 + 5];
-
-		in_prev = in;
-		q_prev = q_cur;
+		SXS_LOAD6(ctx, i, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+		sxs_scale_node(&r, ctx, i, &x);
 	}
-	return up / down;
+	return r.up / r.down;
 }
 
 /* src/min_saxs.c:3-105 with k = sxs_best_scale(c1, c2) as the driver loop sets it (:233-236). */
 SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, double *f, double *g0, double *g1)
 {
 	const double k = sxs_fit_best_scale(ctx, c1, c2);
-	const double *a = ctx->a;
-	const double *q = ctx->qvals;
-	const double mult = ctx->mult;
-
-	double grad0 = 0.0, grad1 = 0.0;
-	const double corr = -mult * (c1 * c1 - 1.0);
-	double G = c1 * c1 * c1 * sxs_fit_exp(ctx, corr * q[0] * q[0]);
-	double G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q[0] * q[0]);
-
-	double xvv, xvd, xvw, xdd, xdw, xww;
-	SXS_LOAD6(ctx, 0, xvv, xvd, xvw, xdd, xdw, xww);
-	double in_prev = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
-	double in_der_c1_prev = -G_der * xvd + 2.0 * G * G_der * xdd - G_der * c2 * xdw;
-	double in_der_c2_prev = xvw - G * xdw + 2.0 * c2 * xww;
-
-	double q_prev = -1.0;
-	double score = 0.0;
-	const double c1_cube = c1 * c1 * c1;
-
+	struct sxs_six x;
+	struct sxs_grad_run r;
+	SXS_LOAD6(ctx, 0, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+	sxs_grad_begin(&r, ctx, c1, c2, k, &x);
 	for (int i = 0; i < ctx->qnum; i++) {
-		const double q_cur = q[i];
-		G = c1_cube * sxs_fit_exp(ctx, corr * q_cur * q_cur);
-		G_der = G * (3.0 / c1 - 2.0 * c1 * mult * q_cur * q_cur);
-
-		SXS_LOAD6(ctx, i, xvv, xvd, xvw, xdd, xdw, xww);
-
-		const double in = xvv - G * xvd + c2 * xvw + G * G * xdd - G * c2 * xdw + c2 * c2 * xww;
-		const double in_der_c1 = G_der * (-xvd + 2.0 * G * xdd - c2 * xdw);
-		const double in_der_c2 = xvw - G * xdw + 2.0 * c2 * xww;
-
-		/* 1 / (q_i - q_{i-1}): from the table when there is one (the same IEEE quotient, computed once per block) */
-#if defined(__CUDA_ARCH__)
-		double buf = ctx->rq[i];
-#else
-		double buf = ctx->rq ? ctx->rq[i] : 1.0 / (q_cur - q_prev);
-#endif
-		const double tan = (in - in_prev) * buf;
-		const double tan_c1_der = (in_der_c1 - in_der_c1_prev) * buf;
-		const double tan_c2_der = (in_der_c2 - in_der_c2_prev) * buf;
-
-		const double a1 = a[i * 6 + 1], a2 = a[i * 6 + 2], a3 = a[i * 6 + 3], a4 = a[i * 6 + 4], a5 = a[i * 6 + 5];
-
-		grad0 += 2.0 * k * (-(in_der_c1 - tan_c1_der * q_cur) * a1 - tan_c1_der * a2 +
-		                    k * ((in - tan * q_cur) * (in_der_c1 - tan_c1_der * q_cur) * a3 +
-		                         (in * tan_c1_der + in_der_c1 * tan - 2.0 * tan * tan_c1_der * q_cur) * a4 +
-		                         tan * tan_c1_der * a5));
-
-		grad1 += 2.0 * k * (-(in_der_c2 - tan_c2_der * q_cur) * a1 - tan_c2_der * a2 +
-		                    k * ((in - tan * q_cur) * (in_der_c2 - tan_c2_der * q_cur) * a3 +
-		                         (in * tan_c2_der + in_der_c2 * tan - 2.0 * tan * tan_c2_der * q_cur) * a4 +
-		                         tan * tan_c2_der * a5));
-
-		buf = in - tan * q_cur;
-		score += a[i * 6] + k * (-2.0 * buf * a1 - 2.0 * tan * a2 +
-		                         k * (buf * buf * a3 + 2.0 * buf * tan * a4 + tan * tan * a5));
-
-		in_prev = in;
-		in_der_c1_prev = in_der_c1;
-		in_der_c2_prev = in_der_c2;
-		q_prev = q_cur;
+		SXS_LOAD6(ctx, i, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+		sxs_grad_node(&r, ctx, i, &x);
 	}
-	*g0 = grad0;
-	*g1 = grad1;
-	*f = score;
+	*g0 = r.grad0;
+	*g1 = r.grad1;
+	*f = r.score;
 }
 
 /* One-pass form of the same objective.  The reference walks q twice per evaluation: once for the optimal scale

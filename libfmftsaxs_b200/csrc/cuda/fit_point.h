@@ -46,6 +46,7 @@ SXS_HD void sxs_fit_point_ex(const double *x, long stride, long qstride, const d
 	ctx.qnum = qnum;
 	ctx.mult = mult;
 	ctx.rq = NULL; /* the serial form divides in the loop */
+	ctx.dq = NULL;
 	ctx.etab = etab; /* NULL on the host: libm's exp itself */
 	ctx.scale = 1.0;
 	ctx.scale = sxs_fit_rescale(&ctx, peak);

@@ -72,6 +72,7 @@ struct lq_state {
 	double f;
 	double ws[3][4], wy[3][4];        /* [variable][correction], correction 1 = oldest */
 	double sy[4][4], ss[4][4], wt[4][4];
+	double sq[4];                     /* sqrt(sy[i][i]): bmv takes these roots six times per call, sy changes once per iteration */
 	double wn1[7][7];                 /* lower triangle of N: rows/cols 1..3 = Y block, 4..6 = S block */
 	double wn[7][7];                  /* upper-triangular factor: blocks at 1..col and LQ_M+1..LQ_M+col */
 	double z[3], r[3], d[3], t[3];
@@ -223,7 +224,7 @@ LQ_FN int lq_bmv(const struct lq_state *s, const double *v1, const double *v2, d
 	LQ_UNROLL
 	for (int i = 1; i <= LQ_M; i++) {
 		if (i <= col) {
-			p1[i] = lq_div(v1[i], lq_sqrt(s->sy[i][i]));
+			p1[i] = lq_div(v1[i], s->sq[i]);
 		}
 	}
 	info = lq_dtrsl_wt(s, p2, 0);
@@ -233,7 +234,7 @@ LQ_FN int lq_bmv(const struct lq_state *s, const double *v1, const double *v2, d
 	LQ_UNROLL
 	for (int i = 1; i <= LQ_M; i++) {
 		if (i <= col) {
-			p1[i] = lq_div(-p1[i], lq_sqrt(s->sy[i][i]));
+			p1[i] = lq_div(-p1[i], s->sq[i]);
 		}
 	}
 	LQ_UNROLL
@@ -1091,6 +1092,10 @@ LQ_FN void lq_matupd(struct lq_state *s, double rr, double dr)
 			s->sy[cc][cc] = dr;
 		}
 	}
+	LQ_UNROLL
+	for (int i = 1; i <= LQ_M; i++) {
+		if (i <= col) s->sq[i] = lq_sqrt(s->sy[i][i]);
+	}
 }
 
 /* T = theta*S'S + L*D^-1*L', Cholesky-factored in place (subalgorithms.c formt, :920-974). */
@@ -1358,6 +1363,7 @@ LQ_FN void lq_begin(struct lq_state *s, double x1, double x2)
 		LQ_UNROLL
 		for (int j = 1; j <= LQ_M; j++) { s->sy[i][j] = 0.0; s->ss[i][j] = 0.0; s->wt[i][j] = 0.0; }
 		s->c1h[i] = 0.0; s->c2h[i] = 0.0;
+		s->sq[i] = 0.0;
 	}
 	LQ_UNROLL
 	for (int i = 1; i <= 2 * LQ_M; i++) {

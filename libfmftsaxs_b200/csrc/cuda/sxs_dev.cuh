@@ -69,24 +69,15 @@ __host__ __device__ inline sxs_pose_digits sxs_key_unpack(int nb, int N, unsigne
 	return d;
 }
 
-/* Cross terms between K3 and K4.  SXS_X_TILED: points are kept in tiles of 32 (one warp of K4); inside a tile the
- * 6*qnum terms are term-major and the 32 points are the fastest index, X[((tile*qnum + q)*6 + k)*32 + lane] — the
- * warp of K4 that owns the tile reads every term with one coalesced 256-byte load.  Otherwise point-major rows
- * X[p*6*qnum + q*6 + k]. */
-#ifndef SXS_X_ROWMAJOR
-#define SXS_X_TILED 1
-#endif
-#ifdef SXS_X_TILED
-__host__ __device__ inline size_t sxs_x_index(long long p, int qnum, int q, int k)
-{
-	return (((size_t)(p >> 5) * qnum + q) * 6 + k) * 32 + (size_t)(p & 31);
-}
-#else
+/* Cross terms between K3 and K4: one contiguous row of 6*qnum doubles per distinct grid point, node-major,
+ * X[(p*qnum + q)*6 + k] (k = VV, VD, VW, DD, DW, WW), 16-byte aligned.  K4 gives every lane its own row and streams it
+ * through a per-lane shared-memory ring with 16-byte asynchronous copies, so a lane can take its next point the moment
+ * its fit ends.  (Round 1 kept tiles of 32 points for coalesced warp loads, which ties the 32 fits of a warp together:
+ * with 2..60 evaluations per fit only 56 % of the lanes were active in the objective, profiles/r2_k4_notes.md.) */
 __host__ __device__ inline size_t sxs_x_index(long long p, int qnum, int q, int k)
 {
 	return ((size_t)p * qnum + q) * 6 + k;
 }
-#endif
 
 /* ---- launchers implemented in sxs_exact.cu (compiled with -fmad=false) ---- */
 

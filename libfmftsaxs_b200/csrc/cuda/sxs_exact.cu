@@ -18,21 +18,13 @@
 #include "sxs_dev.cuh"
 
 #define SXS_HD __host__ __device__ __forceinline__
-#ifndef SXS_X_TILED
 #define SXS_ROWMAJOR_VEC 1
-#endif
 /* The objective is the reference's two-pass form (sxs_fit_eval), bit-identical to it.  -DSXS_FIT_EVAL_FUSED builds the
  * one-pass form of round 1 (algebraically equal, 27 % cheaper per evaluation): on the real 4G9S list it leaves 17 of
  * 1131 / 45 of 70 000 rows beyond 1e-6 in c2 against 3 / 10 for the two-pass form (gpurun_out/r2a_pytest_*.txt), so
  * it is not what ships. */
 #ifdef SXS_FIT_EVAL_FUSED
 #define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory */
-#endif
-#ifndef SXS_XLD
-#define SXS_XLD __ldcs         /* cross-term rows are streamed (evict-first): 49.5 ms */
-#endif
-#if defined(SXS_X_TILED) && defined(__CUDA_ARCH__)
-#define SXS_XLD1(p) __ldcs(p)
 #endif
 #include "fit_point.h"
 
@@ -63,30 +55,165 @@ __device__ __forceinline__ void fit_store(const struct lq_state *st, double *__r
 	res[p * 4 + 3] = (double)st->nfgv;
 }
 
-/* K4.  X comes in tiles of 32 points (sxs_x_index): a warp takes a whole tile, lane = point, and reads every term of
- * every node with one coalesced 256-byte load; a lane whose fit has ended idles until the warp's slowest fit is done,
- * then the warp takes the next tile from the ticket counter.
+/* ---- K4 -------------------------------------------------------------------------------------------------------
+ * Every lane owns one fit: it runs the reverse-communication optimiser (lbfgsb_lean.h, all state in registers) until
+ * the optimiser asks for the objective at a trial (c1, c2); the lanes of a warp that want the objective then evaluate
+ * it together.  A lane whose fit ends takes the next point from the ticket counter at once.
  *
- * Every lane owns one fit and runs the reverse-communication optimiser (lbfgsb_lean.h: all of its state in registers)
- * until it asks for the objective; the objective — two passes over the q nodes like the reference, the bulk of the
- * arithmetic — is evaluated convergently by the lanes that want it (evaluations per fit range from 2 to ~60).
- * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) is run when at least NUM/DEN of the
- * round's waiting fits wait for it, so that it executes with most lanes active.
+ * The objective walks the point's row of 6*qnum cross terms twice (best scale, then f and gradient: the reference's
+ * two passes, src/min_saxs.c:261-319 and :3-105).  The row is streamed from L2/HBM through a per-lane ring in shared
+ * memory with 16-byte asynchronous copies (cp.async, three per node), SXS_FIT_RING nodes ahead of the arithmetic:
+ * r2c ncu of the form with plain loads had 38 % of all stall samples on the two load sites (long scoreboard) at 8
+ * warps per SM.
  *
- * Rounds are per warp by default; -DSXS_FIT_BLOCK_ROUNDS synchronises them over the block (round 1's form, when the
- * optimiser was 3x the code and shared instruction fetch mattered).  Tuning log: profiles/r2_k4_notes.md. */
-#ifndef SXS_X_TILED
-#error "k_fit reads the tiled cross-term layout"
+ * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) runs when NUM/DEN of the warp's waiting
+ * lanes wait for it, so that it executes with most lanes active.  Tuning log: profiles/r2_k4_notes.md. */
+#ifndef SXS_FIT_RING
+#define SXS_FIT_RING 8
 #endif
+
+__device__ __forceinline__ void fit_cp16(unsigned dst_smem, const double *src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void fit_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fit_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/* ring slot j of a lane: 48 bytes at shared address ring + j * SXS_FIT_SLOT_BYTES; the slots of one ring position are
+ * lane-contiguous (48-byte lane stride: conflict-free 16-byte shared loads per quarter warp) */
+#define SXS_FIT_SLOT_BYTES (SXS_FIT_THREADS * 48)
+
+__device__ __forceinline__ void fit_issue(unsigned ring, int slot, const double *row, int node)
+{
+	const unsigned dst = ring + (unsigned)slot * SXS_FIT_SLOT_BYTES;
+	const double *src = row + node * 6;
+	fit_cp16(dst, src);
+	fit_cp16(dst + 16, src + 2);
+	fit_cp16(dst + 32, src + 4);
+}
+
+__device__ __forceinline__ void fit_take(unsigned ring, int slot, double scale, struct sxs_six *x)
+{
+	const unsigned src = ring + (unsigned)slot * SXS_FIT_SLOT_BYTES;
+	double2 p0, p1, p2;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0.x), "=d"(p0.y) : "r"(src));
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p1.x), "=d"(p1.y) : "r"(src + 16));
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p2.x), "=d"(p2.y) : "r"(src + 32));
+	x->vv = p0.x * scale; x->vd = p0.y * scale;
+	x->vw = p1.x * scale; x->dd = p1.y * scale;
+	x->dw = p2.x * scale; x->ww = p2.y * scale;
+}
+
+/* f, g of the fit at (c1, c2): sxs_fit_eval (fit_eval.h) with the row arriving through the ring.  The arithmetic is
+ * that of sxs_scale_* / sxs_grad_* — node 0 is fed to begin() and to the first node() like the serial form.
+ *
+ * The stream has 2 * Qp positions, Qp = qnum rounded up to the ring size: pass 1 over the nodes, padding, pass 2 over
+ * the nodes, padding.  Padding positions are neither copied nor computed; they keep "ring slot = position mod ring
+ * size" a compile-time constant inside the unrolled body.  Position s is requested SXS_FIT_RING - 1 positions ahead
+ * of its use.
+ *
+ * A real call (noinline): the caller holds ~200 registers of optimiser state that are dead weight in here; behind a
+ * call boundary the loops get a register allocation of their own and the state is parked once per evaluation. */
+struct fit_eval_args {
+	const double *row;
+	const double *a, *qvals, *rq, *dq;
+	const uint64_t *etab;
+	unsigned ring;
+	int qnum;
+	double mult, scale;
+};
+
+__device__ __noinline__ void fit_eval_streamed(const struct fit_eval_args *ap, double c1, double c2, double *out3)
+{
+	struct sxs_fit_ctx ctx;
+	ctx.x = ap->row; ctx.stride = 1; ctx.qstride = 6;
+	ctx.a = ap->a; ctx.qvals = ap->qvals; ctx.qnum = ap->qnum; ctx.mult = ap->mult; ctx.scale = ap->scale;
+	ctx.rq = ap->rq; ctx.dq = ap->dq; ctx.etab = ap->etab;
+	const double *row = ap->row;
+	const unsigned ring = ap->ring;
+	const double scale = ap->scale;
+	const int Q = ap->qnum;
+	const int Qp = (Q + SXS_FIT_RING - 1) / SXS_FIT_RING * SXS_FIT_RING;
+
+	/* positions 0 .. RING-2 of pass 1 */
+#pragma unroll
+	for (int t = 0; t < SXS_FIT_RING - 1; t++) {
+		if (t < Q) {
+			fit_issue(ring, t, row, t);
+		}
+		fit_cp_commit();
+	}
+	struct sxs_six x;
+	struct sxs_scale_run sr;
+	struct sxs_grad_run gr;
+	int ahead = SXS_FIT_RING - 1; /* node index (within its pass) of the position requested next; >= Q: padding */
+	bool more = true;             /* positions left to request (false once pass 2 has been requested completely) */
+	/* ---- pass 1: best scale ---- */
+#pragma unroll 1
+	for (int base = 0; base < Qp; base += SXS_FIT_RING) {
+#pragma unroll
+		for (int j = 0; j < SXS_FIT_RING; j++) {
+			const int i = base + j;
+			/* request the position RING-1 ahead into the slot that was consumed one step ago */
+			if (ahead < Q) {
+				fit_issue(ring, (j + SXS_FIT_RING - 1) % SXS_FIT_RING, row, ahead);
+			}
+			fit_cp_commit();
+			ahead = ahead + 1 == Qp ? 0 : ahead + 1;
+			fit_cp_wait<SXS_FIT_RING - 1>();
+			if (i < Q) {
+				fit_take(ring, j, scale, &x);
+				if (i == 0) {
+					sxs_scale_begin(&sr, &ctx, c1, c2, &x);
+				}
+				sxs_scale_node(&sr, &ctx, i, &x);
+			}
+		}
+	}
+	const double k = sr.up / sr.down;
+	/* ---- pass 2: f and gradient with k frozen; its first RING-1 positions were requested during pass 1 ---- */
+#pragma unroll 1
+	for (int base = 0; base < Qp; base += SXS_FIT_RING) {
+#pragma unroll
+		for (int j = 0; j < SXS_FIT_RING; j++) {
+			const int i = base + j;
+			if (more && ahead < Q) {
+				fit_issue(ring, (j + SXS_FIT_RING - 1) % SXS_FIT_RING, row, ahead);
+			}
+			fit_cp_commit();
+			if (ahead + 1 == Qp) {
+				more = false; /* the stream ends with pass 2: nothing lies beyond its last position */
+				ahead = 0;
+			} else {
+				ahead = ahead + 1;
+			}
+			fit_cp_wait<SXS_FIT_RING - 1>();
+			if (i < Q) {
+				fit_take(ring, j, scale, &x);
+				if (i == 0) {
+					sxs_grad_begin(&gr, &ctx, c1, c2, k, &x);
+				}
+				sxs_grad_node(&gr, &ctx, i, &x);
+			}
+		}
+	}
+	fit_cp_wait<0>();
+	out3[0] = gr.score;
+	out3[1] = gr.grad0;
+	out3[2] = gr.grad1;
+}
+
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {
-	extern __shared__ double s_tab[]; /* [6*qnum] moments, [qnum] q grid, [qnum] reciprocal node spacings, exp table */
-	double *s_a = s_tab;
-	double *s_q = s_tab + 6 * qnum;
-	double *s_rq = s_tab + 7 * qnum;
-	uint64_t *s_etab = reinterpret_cast<uint64_t *>(s_tab + 8 * qnum);
+	extern __shared__ __align__(16) double s_tab[]; /* ring, [6*qnum] moments, [qnum] q grid, [qnum] reciprocal spacings, exp table */
+	double *s_ring = s_tab;
+	double *s_a = s_tab + (size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6;
+	double *s_q = s_a + 6 * qnum;
+	double *s_rq = s_a + 7 * qnum;
+	double *s_dq = s_a + 8 * qnum;
+	uint64_t *s_etab = reinterpret_cast<uint64_t *>(s_a + 9 * qnum);
 	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
 		s_etab[i] = d_exp_tab[i];
 	}
@@ -96,14 +223,19 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	for (int i = threadIdx.x; i < qnum; i += blockDim.x) {
 		s_q[i] = qvals[i];
 		s_rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
+		s_dq[i] = qvals[i] - (i > 0 ? qvals[i - 1] : -1.0);
 	}
 	__syncthreads();
 
 	struct lq_state st;
 	struct sxs_fit_ctx ctx;
-	ctx.stride = 32; ctx.qstride = 6 * 32; ctx.a = s_a;
+	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a;
 	ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
-	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq; ctx.etab = s_etab;
+	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq; ctx.dq = s_dq; ctx.etab = s_etab;
+	struct fit_eval_args ea;
+	ea.a = s_a; ea.qvals = s_q; ea.rq = s_rq; ea.dq = s_dq; ea.etab = s_etab;
+	ea.ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 48u;
+	ea.qnum = qnum; ea.mult = mult; ea.scale = 1.0; ea.row = X;
 	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
 	(void)sum_a0;
 	long long p = -1;
@@ -121,35 +253,9 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 				fit_store(&st, res, p);
 			}
 		}
-		/* (2) iteration boundary, when enough of the round's fits wait for it */
-#ifdef SXS_FIT_BLOCK_ROUNDS
-		const int n_b = __syncthreads_count(mode == WANT_B);
-		const int n_e = __syncthreads_count(mode == WANT_EVAL);
-#else
-		const int n_b = __popc(__ballot_sync(0xffffffffu, mode == WANT_B));
-		const int n_e = __popc(__ballot_sync(0xffffffffu, mode == WANT_EVAL));
-#endif
-		if (n_b > 0 && (n_e == 0 || n_b * SXS_FIT_BATCH_DEN >= (n_b + n_e) * SXS_FIT_BATCH_NUM)) {
-			if (mode == WANT_B) {
-				const int r = lq_step_b(&st, SXS_FIT_PGTOL, SXS_FIT_TOL);
-				mode = (r == LQ_NEED_EVAL) ? WANT_EVAL : FREE;
-				if (r == LQ_DONE) {
-					fit_store(&st, res, p);
-				}
-			}
-		}
-		/* (3) a warp takes a whole tile of 32 points when all its lanes are free: lane = point inside the tile */
-		const bool warp_free = __all_sync(0xffffffffu, mode == FREE);
-		if (warp_free && !drained) {
-			unsigned long long tile = 0;
-			if ((threadIdx.x & 31) == 0) {
-				tile = atomicAdd(ticket, 1ull);
-			}
-			tile = __shfl_sync(0xffffffffu, tile, 0);
-			p = (long long)(tile * 32ull + (threadIdx.x & 31));
-			if ((long long)(tile * 32ull) >= npts) {
-				drained = true;
-			}
+		/* (2) free lanes take the next point from the ticket counter */
+		if (mode == FREE && !drained) {
+			p = (long long)atomicAdd(ticket, 1ull);
 			if (p < npts) {
 				ctx.x = X + sxs_x_index(p, qnum, 0, 0);
 				ctx.scale = 1.0;
@@ -162,23 +268,38 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 				if (r == LQ_DONE) {
 					fit_store(&st, res, p);
 				}
+			} else {
+				drained = true;
+			}
+		}
+		/* (3) iteration boundary, when enough of the warp's waiting fits wait for it */
+		const int n_b = __popc(__ballot_sync(0xffffffffu, mode == WANT_B));
+		const int n_e = __popc(__ballot_sync(0xffffffffu, mode == WANT_EVAL));
+		if (n_b > 0 && (n_e == 0 || n_b * SXS_FIT_BATCH_DEN >= (n_b + n_e) * SXS_FIT_BATCH_NUM)) {
+			if (mode == WANT_B) {
+				const int r = lq_step_b(&st, SXS_FIT_PGTOL, SXS_FIT_TOL);
+				mode = (r == LQ_NEED_EVAL) ? WANT_EVAL : FREE;
+				if (r == LQ_DONE) {
+					fit_store(&st, res, p);
+				}
 			}
 		}
 		/* (4) the objective */
-#ifdef SXS_FIT_BLOCK_ROUNDS
-		if (!__syncthreads_or(mode != FREE)) {
-			break;
-		}
-#else
 		if (!__any_sync(0xffffffffu, mode != FREE)) {
-			if (drained) {
+			if (__all_sync(0xffffffffu, drained)) {
 				break;
 			}
 			continue;
 		}
-#endif
 		if (mode == WANT_EVAL) {
-			SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+#ifdef SXS_FIT_EVAL_FUSED
+			sxs_fit_eval_fused(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+#else
+			double fg[3];
+			ea.row = ctx.x; ea.scale = ctx.scale;
+			fit_eval_streamed(&ea, st.x[1], st.x[2], fg);
+			st.f = fg[0]; st.g[1] = fg[1]; st.g[2] = fg[2];
+#endif
 			mode = EVALUATED;
 		}
 		__syncwarp();
@@ -198,7 +319,8 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	int dev = 0, sms = 148, per_sm = 4;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const size_t shm = sizeof(double) * 8 * qnum + sizeof(uint64_t) * SXS_EXP_TABLE_ENTRIES;
+	const size_t shm = sizeof(double) * ((size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6 + 9 * qnum) + sizeof(uint64_t) * SXS_EXP_TABLE_ENTRIES;
+	SXS_CK(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
 	if (per_sm < 1) per_sm = 1;
 	if (getenv("SXS_FIT_BLOCKS_PER_SM")) { /* tuning only */
@@ -237,7 +359,7 @@ extern "C" int sxs_cuda_fit_profiles(int device, const double *cross, long long 
 	unsigned long long *d_ticket = NULL;
 	const size_t nx = (size_t)npts * 6 * qnum;
 	SXS_CK(cudaMalloc(&d_cross, sizeof(double) * nx));
-	SXS_CK(cudaMalloc(&d_x, sizeof(double) * (size_t)((npts + 31) / 32 * 32) * 6 * qnum));
+	SXS_CK(cudaMalloc(&d_x, sizeof(double) * nx));
 	SXS_CK(cudaMalloc(&d_a, sizeof(double) * 6 * qnum));
 	SXS_CK(cudaMalloc(&d_q, sizeof(double) * qnum));
 	SXS_CK(cudaMalloc(&d_res, sizeof(double) * 4 * npts));
@@ -266,11 +388,12 @@ __global__ void k_fit_eval(const double *__restrict__ cross, const double *__res
 	ctx.x = cross; /* point-major row x[q*6 + k] */
 	ctx.stride = 1;
 	ctx.qstride = 6;
-	double rq[SXS_FIT_MAXQ];
+	double rq[SXS_FIT_MAXQ], dq[SXS_FIT_MAXQ];
 	for (int i = 0; i < qnum; i++) {
-		rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
+		dq[i] = qvals[i] - (i > 0 ? qvals[i - 1] : -1.0);
+		rq[i] = 1.0 / dq[i];
 	}
-	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = rq; ctx.etab = d_exp_tab;
+	ctx.a = a; ctx.qvals = qvals; ctx.qnum = qnum; ctx.mult = mult; ctx.scale = 1.0; ctx.rq = rq; ctx.dq = dq; ctx.etab = d_exp_tab;
 	out4[0] = sxs_fit_best_scale(&ctx, c1, c2);
 	sxs_fit_eval(&ctx, c1, c2, &out4[1], &out4[2], &out4[3]);
 }

@@ -85,7 +85,7 @@ struct sxs_cuda_plan {
 	/* workspace (grow-only) */
 	double2 *d_T;  size_t cap_T;   /* [zg][q][m][l][l1] */
 	double2 *d_St; size_t cap_St;  /* [zg*nb slabs][q][c][ml][g], rows padded like At */
-	double *d_X;   size_t cap_X;   /* cross terms handed from K3 to K4, tiles of 32 points (sxs_x_index) */
+	double *d_X;   size_t cap_X;   /* cross terms handed from K3 to K4, one row per point (sxs_x_index) */
 	unsigned long long *d_ticket;
 	double *d_res; size_t cap_res; /* [points][4] */
 	unsigned long long *d_keys, *d_keys_sorted, *d_pkeys;
@@ -791,20 +791,10 @@ k_cross(int L, int qnum, const unsigned long long *__restrict__ pkeys, long long
 #pragma unroll
 	for (int k = 0; k < K; k++) {
 		if (k < members) {
-#ifdef SXS_X_TILED
-			double *xo = X + sxs_x_index(p + k - xbase, qnum, q, 0); /* consecutive points: 256-byte stores per warp */
-			xo[0 * 32] = c0 + 2.0 * f[k][0];
-			xo[1 * 32] = c1 + 2.0 * f[k][1];
-			xo[2 * 32] = c2 + 2.0 * f[k][2];
-			xo[3 * 32] = c3 + 2.0 * f[k][3];
-			xo[4 * 32] = c4 + 2.0 * f[k][4];
-			xo[5 * 32] = c5 + 2.0 * f[k][5];
-#else
-			double2 *xo = reinterpret_cast<double2 *>(X + ((size_t)(p + k - xbase) * qnum + q) * 6);
+			double2 *xo = reinterpret_cast<double2 *>(X + sxs_x_index(p + k - xbase, qnum, q, 0));
 			xo[0] = make_double2(c0 + 2.0 * f[k][0], c1 + 2.0 * f[k][1]);
 			xo[1] = make_double2(c2 + 2.0 * f[k][2], c3 + 2.0 * f[k][3]);
 			xo[2] = make_double2(c4 + 2.0 * f[k][4], c5 + 2.0 * f[k][5]);
-#endif
 		}
 	}
 }
@@ -1099,7 +1089,7 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 	}
 	if (ensure(&p->d_St, &p->cap_St, slab_elems * nb * (size_t)zg_max)) return -1;
 	if (ensure(&p->d_T, &p->cap_T, (size_t)zg_max * Q * nb * nb * nb)) return -1;
-	if (ensure(&p->d_X, &p->cap_X, (size_t)((chunk_max + 31) / 32 * 32) * 6 * Q)) return -1;
+	if (ensure(&p->d_X, &p->cap_X, (size_t)chunk_max * 6 * Q)) return -1;
 	if (p->d_slab_flag == NULL || p->cap_slab < zg_max * nb + zg_max) {
 		if (p->d_slab_flag) cudaFree(p->d_slab_flag);
 		SXS_CK(cudaMalloc(&p->d_slab_flag, sizeof(int) * (zg_max * nb + zg_max)));

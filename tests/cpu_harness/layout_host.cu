@@ -54,7 +54,7 @@ int main()
 		hi = {4095, nb - 1, nb - 1, N - 1, N - 1, N - 1};
 		if (sxs_key_pack(nb, N, hi) >= 0xFFFFFFFFFFFFFFFFull / 2) return fail("key range", L);
 	}
-	/* hand-off layout: a bijection from (point, q, k) onto [0, tiles * qnum * 6 * 32); a tile's 32 points are the fastest index */
+	/* hand-off layout: a bijection from (point, q, k) onto [0, npts * qnum * 6); the six terms of a node are contiguous */
 	for (int qnum : {1, 50, 100}) {
 		const long long npts = 32 * 5 + 7, tiles = (npts + 31) / 32;
 		std::vector<char> seen((size_t)tiles * qnum * 6 * 32, 0);
@@ -64,10 +64,8 @@ int main()
 					const size_t i = sxs_x_index(p, qnum, q, k);
 					if (i >= seen.size() || seen[i]) return fail("x index bijection", qnum);
 					seen[i] = 1;
-#ifdef SXS_X_TILED
-					if (p % 32 != 31 && p + 1 < npts && sxs_x_index(p + 1, qnum, q, k) != i + 1) return fail("x index lane stride", qnum);
-					if (k < 5 && sxs_x_index(p, qnum, q, k + 1) != i + 32) return fail("x index term stride", qnum);
-#endif
+					if (k < 5 && sxs_x_index(p, qnum, q, k + 1) != i + 1) return fail("x index term stride", qnum);
+					if (i % 2 == 0 && k % 2 != 0) return fail("x index 16-byte pairs", qnum);
 				}
 			}
 		}

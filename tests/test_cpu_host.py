@@ -478,9 +478,17 @@ chk = torch.tensor([float(allt.sum())], dtype=torch.float64)
 lst = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
 dist.all_gather(lst, chk)
 same = all(abs(float(x) - float(chk)) == 0.0 for x in lst)
+# (3) strong scaling plumbing: one list split by z range, padded shards all-gathered, index copy into input order
+gsh = sd.RowShardGather(idx, L, len(zv), world, rank)
+mine = gsh.my_rows
+gsh.local[:, :len(mine)] = torch.from_numpy(np.stack([mine * 1.0, mine * 2.0 + 0.5, -mine * 1.0]))
+tab = gsh.gather().numpy()
+ar = np.arange(len(idx))
+strong_ok = np.array_equal(tab[0], ar * 1.0) and np.array_equal(tab[1], ar * 2.0 + 0.5) and np.array_equal(tab[2], -ar * 1.0)
+strong_ok = strong_ok and sum(len(r) for r in gsh.rows) == len(idx) and all(len(r) > 0 for r in gsh.rows)
 dist.barrier()
 dist.destroy_process_group()
-sys.exit(0 if (ok and same) else 3)
+sys.exit(0 if (ok and same and strong_ok) else 3)
 '''
 
 

@@ -150,6 +150,39 @@ def test_properties_on_bench_workload():
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(base, tight))
 
 
+def test_one_list_over_two_devices_in_process():
+    """sxs_compute_saxs_scores with SXS_CUDA_DEVICES=0,1 (one host thread per device, each extracting the rows of its own
+    z range — the replacement of `mpirun -np 2 correlate`, tools/correlate.c:140-147,295-356) returns the bits one
+    device returns, rows outside the z table untouched; needs two GPUs (gpurun --gpus 2)"""
+    if capi.device_count() < 2:
+        pytest.skip("one CUDA device only")
+    G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+    R = np.load(os.path.join(GOLD, "golden_real70k.npz"))
+    q, L = G["qvals"], int(G["L"])
+    nb, N = L + 1, 2 * L + 1
+    idx = R["index"].copy()
+    idx = np.concatenate([idx[:40000], np.array([-3], dtype=idx.dtype), idx[40000:]])
+    init = (np.full(len(idx), 7.0), np.full(len(idx), 8.0), np.full(len(idx), 9.0))
+    old = os.environ.get("SXS_CUDA_DEVICES")
+    try:
+        os.environ["SXS_CUDA_DEVICES"] = "0"
+        one = capi.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, R["zvals"], L, init=init)
+        os.environ["SXS_CUDA_DEVICES"] = "0,1"
+        two = capi.scores(idx, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, R["zvals"], L, init=init)
+        both64 = capi.scores(idx.astype(np.int64), G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, R["zvals"], L, init=init)
+    finally:
+        if old is None:
+            os.environ.pop("SXS_CUDA_DEVICES", None)
+        else:
+            os.environ["SXS_CUDA_DEVICES"] = old
+    assert all(np.array_equal(x, y) for x, y in zip(one, two))
+    assert all(np.array_equal(x, y) for x, y in zip(one, both64))
+    assert one[0][40000] == 7.0 and two[1][40000] == 8.0 and two[2][40000] == 9.0
+    keep = np.arange(len(idx)) != 40000
+    parity.check("real list over two devices", tuple(x[keep] for x in two), (R["scores"], R["c1"], R["c2"]),
+                 sens=(R["sens_scores"], R["sens_c1"], R["sens_c2"]))
+
+
 def test_translation_kernels_agree_bit_for_bit():
     """K2c: the register-tiled translation (4 x 2 outputs per thread) writes the same St as the one-output-per-thread
     form (SXS_TRANSLATE_V1) — scores, c1, c2 are equal to the last bit — at L = 15 and at L = 30 / Q = 100"""
