@@ -57,6 +57,14 @@ static inline double sxs_exp_dbl_(uint64_t u) { double d; memcpy(&d, &u, 8); ret
 #define SXS_EXP_DBL(u) sxs_exp_dbl_(u)
 #endif
 
+/* |x| >= 512, inf, nan: never reached by the fit (|x| < 0.02); a real call on the device so that the math library's
+ * exp is not expanded inside the objective's loops (instruction-cache footprint) */
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ double sxs_exp_out_of_range(double x) { return exp(x); }
+#else
+static inline double sxs_exp_out_of_range(double x) { return exp(x); }
+#endif
+
 /* tab: the SXS_EXP_TABLE_ENTRIES words of exp_table.h (shared memory on the device) */
 SXS_HD double sxs_exp_glibc(double x, const uint64_t *tab)
 {
@@ -65,7 +73,7 @@ SXS_HD double sxs_exp_glibc(double x, const uint64_t *tab)
 		if (abstop < 0x3c9u) {
 			return SXS_EXP_ADD(1.0, x); /* |x| < 2^-54, including +-0 */
 		}
-		return exp(x); /* |x| >= 512, inf, nan: not on this path */
+		return sxs_exp_out_of_range(x);
 	}
 	double kd = SXS_EXP_FMA(x, SXS_EXP_INVLN2N, SXS_EXP_SHIFT);
 	const uint64_t ki = SXS_EXP_BITS(kd);

@@ -28,7 +28,6 @@
 #endif
 #include "fit_point.h"
 
-#define SXS_FIT_MAXQ 512
 #ifndef SXS_FIT_THREADS
 #define SXS_FIT_THREADS 256
 #endif
@@ -46,6 +45,31 @@
 
 /* 2^(k/128) table of the libm-faithful exp (exp_glibc.h); k_fit copies it to shared memory */
 __device__ const uint64_t d_exp_tab[SXS_EXP_TABLE_ENTRIES] = SXS_EXP_TABLE_INIT;
+
+/* Per-block tables of the fit, statically placed so that every device function addresses them as shared memory
+ * (through a generic pointer handed across a call the objective's loads became generic LD + R2UR/UMOV address
+ * traffic: 20 % of its instructions, r2g ncu). */
+#define SXS_FIT_MAXQ 128
+__shared__ double fs_a[6 * SXS_FIT_MAXQ];   /* compressed experiment a[q*6 + 0..5] */
+__shared__ double fs_q[SXS_FIT_MAXQ];       /* q grid */
+__shared__ double fs_rq[SXS_FIT_MAXQ];      /* 1 / (q_i - q_{i-1}) */
+__shared__ double fs_dq[SXS_FIT_MAXQ];      /* q_i - q_{i-1}, q_{-1} = -1 */
+__shared__ uint64_t fs_etab[SXS_EXP_TABLE_ENTRIES];
+
+__device__ __forceinline__ void fit_tables_fill(const double *a, const double *qvals, int qnum)
+{
+	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
+		fs_etab[i] = d_exp_tab[i];
+	}
+	for (int i = threadIdx.x; i < 6 * qnum; i += blockDim.x) {
+		fs_a[i] = a[i];
+	}
+	for (int i = threadIdx.x; i < qnum; i += blockDim.x) {
+		fs_q[i] = qvals[i];
+		fs_dq[i] = qvals[i] - (i > 0 ? qvals[i - 1] : -1.0);
+		fs_rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
+	}
+}
 
 __device__ __forceinline__ void fit_store(const struct lq_state *st, double *__restrict__ res, long long p)
 {
@@ -67,9 +91,12 @@ __device__ __forceinline__ void fit_store(const struct lq_state *st, double *__r
  * warps per SM.
  *
  * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) runs when NUM/DEN of the warp's waiting
- * lanes wait for it, so that it executes with most lanes active.  Tuning log: profiles/r2_k4_notes.md. */
+ * lanes wait for it, so that it executes with most lanes active.  Tuning log: profiles/r2_k4_notes.md — including a
+ * scheduled form (fits as slots of the block with their state in shared memory / an L2 scratch, warps as workers
+ * on an objective queue and an iteration-boundary queue: 31.8 of 32 lanes in the objective) that ran at the same time
+ * per fit with 6x the DRAM traffic and was not kept. */
 #ifndef SXS_FIT_RING
-#define SXS_FIT_RING 8
+#define SXS_FIT_RING 4
 #endif
 
 __device__ __forceinline__ void fit_cp16(unsigned dst_smem, const double *src)
@@ -107,96 +134,95 @@ __device__ __forceinline__ void fit_take(unsigned ring, int slot, double scale, 
 /* f, g of the fit at (c1, c2): sxs_fit_eval (fit_eval.h) with the row arriving through the ring.  The arithmetic is
  * that of sxs_scale_* / sxs_grad_* — node 0 is fed to begin() and to the first node() like the serial form.
  *
- * The stream has 2 * Qp positions, Qp = qnum rounded up to the ring size: pass 1 over the nodes, padding, pass 2 over
- * the nodes, padding.  Padding positions are neither copied nor computed; they keep "ring slot = position mod ring
- * size" a compile-time constant inside the unrolled body.  Position s is requested SXS_FIT_RING - 1 positions ahead
- * of its use.
+ * The stream is the row twice (pass 1, pass 2); position s is requested SXS_FIT_RING - 1 positions ahead of its use.
+ * The node loops are ROLLED on purpose: unrolled by the ring size (compile-time slots) the kernel grew to 10 500 SASS
+ * instructions and ran 2.5x slower with 12 stall cycles per issue in "no instruction" (instruction-cache misses,
+ * profiles/r2_k4_notes.md); ring slot and row pointer advance by pointer increments instead.
  *
- * A real call (noinline): the caller holds ~200 registers of optimiser state that are dead weight in here; behind a
- * call boundary the loops get a register allocation of their own and the state is parked once per evaluation. */
+ * SXS_FIT_EVAL_CALL: a real call (noinline) — the caller holds ~200 registers of optimiser state that are dead weight
+ * in here; behind a call boundary the loops get a register allocation of their own. */
 struct fit_eval_args {
 	const double *row;
-	const double *a, *qvals, *rq, *dq;
-	const uint64_t *etab;
 	unsigned ring;
 	int qnum;
 	double mult, scale;
 };
 
-__device__ __noinline__ void fit_eval_streamed(const struct fit_eval_args *ap, double c1, double c2, double *out3)
+#ifdef SXS_FIT_EVAL_INLINE
+#define SXS_FIT_EVAL_LINKAGE __device__ __forceinline__
+#else
+#define SXS_FIT_EVAL_LINKAGE __device__ __noinline__
+#endif
+
+SXS_FIT_EVAL_LINKAGE void fit_eval_streamed(const struct fit_eval_args *ap, double c1, double c2, double *out3)
 {
 	struct sxs_fit_ctx ctx;
 	ctx.x = ap->row; ctx.stride = 1; ctx.qstride = 6;
-	ctx.a = ap->a; ctx.qvals = ap->qvals; ctx.qnum = ap->qnum; ctx.mult = ap->mult; ctx.scale = ap->scale;
-	ctx.rq = ap->rq; ctx.dq = ap->dq; ctx.etab = ap->etab;
+	ctx.a = fs_a; ctx.qvals = fs_q; ctx.qnum = ap->qnum; ctx.mult = ap->mult; ctx.scale = ap->scale;
+	ctx.rq = fs_rq; ctx.dq = fs_dq; ctx.etab = fs_etab;
 	const double *row = ap->row;
-	const unsigned ring = ap->ring;
+	const unsigned ring = ap->ring, ring_end = ap->ring + SXS_FIT_RING * SXS_FIT_SLOT_BYTES;
 	const double scale = ap->scale;
 	const int Q = ap->qnum;
-	const int Qp = (Q + SXS_FIT_RING - 1) / SXS_FIT_RING * SXS_FIT_RING;
 
-	/* positions 0 .. RING-2 of pass 1 */
+	/* positions 0 .. RING-2 */
+	{
+		const int total = 2 * Q;
 #pragma unroll
-	for (int t = 0; t < SXS_FIT_RING - 1; t++) {
-		if (t < Q) {
-			fit_issue(ring, t, row, t);
+		for (int t = 0; t < SXS_FIT_RING - 1; t++) {
+			if (t < total) {
+				fit_issue(ring, t, row, t < Q ? t : t - Q);
+			}
+			fit_cp_commit();
 		}
-		fit_cp_commit();
 	}
 	struct sxs_six x;
 	struct sxs_scale_run sr;
 	struct sxs_grad_run gr;
-	int ahead = SXS_FIT_RING - 1; /* node index (within its pass) of the position requested next; >= Q: padding */
-	bool more = true;             /* positions left to request (false once pass 2 has been requested completely) */
+	unsigned cur = ring;                                            /* slot of the position being consumed */
+	unsigned nxt = ring + (SXS_FIT_RING - 1) * SXS_FIT_SLOT_BYTES;  /* slot of the position being requested */
+	const double *src = row + ((SXS_FIT_RING - 1) % Q) * 6;         /* its place in the row */
+	const double *row_end = row + Q * 6;
+	int left = 2 * Q - (SXS_FIT_RING - 1);                          /* positions still to request */
+#define SXS_FIT_STEP()                                                         \
+	do {                                                                       \
+		if (left > 0) {                                                        \
+			fit_cp16(nxt, src);                                                \
+			fit_cp16(nxt + 16, src + 2);                                       \
+			fit_cp16(nxt + 32, src + 4);                                       \
+		}                                                                      \
+		fit_cp_commit();                                                       \
+		left--;                                                                \
+		src += 6;                                                              \
+		if (src == row_end) src = row;                                         \
+		nxt += SXS_FIT_SLOT_BYTES;                                             \
+		if (nxt == ring_end) nxt = ring;                                       \
+		fit_cp_wait<SXS_FIT_RING - 1>();                                       \
+		fit_take(cur, 0, scale, &x);                                           \
+		cur += SXS_FIT_SLOT_BYTES;                                             \
+		if (cur == ring_end) cur = ring;                                       \
+	} while (0)
+
 	/* ---- pass 1: best scale ---- */
+	SXS_FIT_STEP();
+	sxs_scale_begin(&sr, &ctx, c1, c2, &x);
+	sxs_scale_node(&sr, &ctx, 0, &x);
 #pragma unroll 1
-	for (int base = 0; base < Qp; base += SXS_FIT_RING) {
-#pragma unroll
-		for (int j = 0; j < SXS_FIT_RING; j++) {
-			const int i = base + j;
-			/* request the position RING-1 ahead into the slot that was consumed one step ago */
-			if (ahead < Q) {
-				fit_issue(ring, (j + SXS_FIT_RING - 1) % SXS_FIT_RING, row, ahead);
-			}
-			fit_cp_commit();
-			ahead = ahead + 1 == Qp ? 0 : ahead + 1;
-			fit_cp_wait<SXS_FIT_RING - 1>();
-			if (i < Q) {
-				fit_take(ring, j, scale, &x);
-				if (i == 0) {
-					sxs_scale_begin(&sr, &ctx, c1, c2, &x);
-				}
-				sxs_scale_node(&sr, &ctx, i, &x);
-			}
-		}
+	for (int i = 1; i < Q; i++) {
+		SXS_FIT_STEP();
+		sxs_scale_node(&sr, &ctx, i, &x);
 	}
 	const double k = sr.up / sr.down;
-	/* ---- pass 2: f and gradient with k frozen; its first RING-1 positions were requested during pass 1 ---- */
+	/* ---- pass 2: f and gradient with k frozen ---- */
+	SXS_FIT_STEP();
+	sxs_grad_begin(&gr, &ctx, c1, c2, k, &x);
+	sxs_grad_node(&gr, &ctx, 0, &x);
 #pragma unroll 1
-	for (int base = 0; base < Qp; base += SXS_FIT_RING) {
-#pragma unroll
-		for (int j = 0; j < SXS_FIT_RING; j++) {
-			const int i = base + j;
-			if (more && ahead < Q) {
-				fit_issue(ring, (j + SXS_FIT_RING - 1) % SXS_FIT_RING, row, ahead);
-			}
-			fit_cp_commit();
-			if (ahead + 1 == Qp) {
-				more = false; /* the stream ends with pass 2: nothing lies beyond its last position */
-				ahead = 0;
-			} else {
-				ahead = ahead + 1;
-			}
-			fit_cp_wait<SXS_FIT_RING - 1>();
-			if (i < Q) {
-				fit_take(ring, j, scale, &x);
-				if (i == 0) {
-					sxs_grad_begin(&gr, &ctx, c1, c2, k, &x);
-				}
-				sxs_grad_node(&gr, &ctx, i, &x);
-			}
-		}
+	for (int i = 1; i < Q; i++) {
+		SXS_FIT_STEP();
+		sxs_grad_node(&gr, &ctx, i, &x);
 	}
+#undef SXS_FIT_STEP
 	fit_cp_wait<0>();
 	out3[0] = gr.score;
 	out3[1] = gr.grad0;
@@ -207,36 +233,19 @@ __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
       int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
 {
-	extern __shared__ __align__(16) double s_tab[]; /* ring, [6*qnum] moments, [qnum] q grid, [qnum] reciprocal spacings, exp table */
-	double *s_ring = s_tab;
-	double *s_a = s_tab + (size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6;
-	double *s_q = s_a + 6 * qnum;
-	double *s_rq = s_a + 7 * qnum;
-	double *s_dq = s_a + 8 * qnum;
-	uint64_t *s_etab = reinterpret_cast<uint64_t *>(s_a + 9 * qnum);
-	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
-		s_etab[i] = d_exp_tab[i];
-	}
-	for (int i = threadIdx.x; i < 6 * qnum; i += blockDim.x) {
-		s_a[i] = a[i];
-	}
-	for (int i = threadIdx.x; i < qnum; i += blockDim.x) {
-		s_q[i] = qvals[i];
-		s_rq[i] = 1.0 / (qvals[i] - (i > 0 ? qvals[i - 1] : -1.0));
-		s_dq[i] = qvals[i] - (i > 0 ? qvals[i - 1] : -1.0);
-	}
+	extern __shared__ __align__(16) double s_ring[]; /* the lanes' row rings; the tables are static (fs_*) */
+	fit_tables_fill(a, qvals, qnum);
 	__syncthreads();
 
 	struct lq_state st;
 	struct sxs_fit_ctx ctx;
-	ctx.stride = 1; ctx.qstride = 6; ctx.a = s_a;
-	ctx.qvals = s_q; ctx.qnum = qnum; ctx.mult = mult;
-	ctx.x = X; ctx.scale = 1.0; ctx.rq = s_rq; ctx.dq = s_dq; ctx.etab = s_etab;
+	ctx.stride = 1; ctx.qstride = 6; ctx.a = fs_a;
+	ctx.qvals = fs_q; ctx.qnum = qnum; ctx.mult = mult;
+	ctx.x = X; ctx.scale = 1.0; ctx.rq = fs_rq; ctx.dq = fs_dq; ctx.etab = fs_etab;
 	struct fit_eval_args ea;
-	ea.a = s_a; ea.qvals = s_q; ea.rq = s_rq; ea.dq = s_dq; ea.etab = s_etab;
 	ea.ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 48u;
 	ea.qnum = qnum; ea.mult = mult; ea.scale = 1.0; ea.row = X;
-	const double sum_a0 = sxs_fit_sum_a0(s_a, qnum);
+	const double sum_a0 = sxs_fit_sum_a0(fs_a, qnum);
 	(void)sum_a0;
 	long long p = -1;
 	bool drained = false;
@@ -319,7 +328,7 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	int dev = 0, sms = 148, per_sm = 4;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	const size_t shm = sizeof(double) * ((size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6 + 9 * qnum) + sizeof(uint64_t) * SXS_EXP_TABLE_ENTRIES;
+	const size_t shm = sizeof(double) * ((size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6);
 	SXS_CK(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);
 	if (per_sm < 1) per_sm = 1;

@@ -163,3 +163,64 @@ def make(name, seed=20240917, nrot=None, nz=None):
     idx = make_pose_indices(cfg["L"], zvals, cfg["nrot"], seed + 3)
     return dict(name=name, L=cfg["L"], qvals=make_qvals(cfg["qnum"]), zvals=np.asarray(zvals, dtype=np.float64),
                 rec=rec, lig=lig, index=idx, seed=seed)
+
+
+# ------------------------------------------------------------------ BASELINE config 1 (examples/run_correlate.sh)
+
+def _splitmix64(seed, n):
+    """n 64-bit outputs of the splitmix64 stream started at `seed` (vectorised)"""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * np.arange(1, n + 1, dtype=np.uint64)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def _uniform01(seed, n):
+    return (_splitmix64(seed, n) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+
+
+def _normals(seed, n):
+    u = _uniform01(seed, 2 * n)
+    return np.sqrt(-2.0 * np.log(1.0 - u[:n])) * np.cos(2.0 * np.pi * u[n:])
+
+
+def make_config1(rec_xyz, lig_xyz, nrot=70000, nfiles=3, seed=0x5A170001, z_lo=20, z_hi=45):
+    """The inputs examples/run_correlate.sh needs and the reference does not ship (.MISSING_LARGE_BLOBS): a rotation
+    set of `nrot` matrices and `nfiles` ft files of `nrot` rows each ("Config 1").
+
+    rotation k   = unit quaternion from a splitmix64 stream (seed 0x5A170001), written as an rm file row
+    ft row k     = rotation index k (each rotation once per file, like the real PIPER fixture), translation
+                   t = z u - ref_lig with u a seeded unit vector (|u_z| <= 0.999) and integer z ~ U{z_lo..z_hi};
+                   ref_lig = ligand centroid - receptor centre of extrema, both in the input frame
+    Returns (rot [nrot][9], [ (rot_index, t[3], z, u) per file ]).
+    """
+    qn = _normals(seed, 4 * nrot).reshape(nrot, 4)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    w, x, y, z = qn.T
+    rot = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                    2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                    2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)
+    rec_c = 0.5 * (rec_xyz.min(0) + rec_xyz.max(0))
+    ref_lig = lig_xyz.mean(0) - rec_c
+    files = []
+    for f in range(nfiles):
+        s = seed + 7919 * (f + 1)
+        u = _normals(s, 3 * nrot).reshape(nrot, 3)
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        bad = np.abs(u[:, 2]) > 0.999
+        u[bad] = np.array([0.6, 0.0, 0.8])
+        zz = z_lo + (_splitmix64(s + 1, nrot) % np.uint64(z_hi - z_lo + 1)).astype(np.int64)
+        t = zz[:, None] * u - ref_lig
+        files.append(dict(rot=np.arange(nrot), t=t, z=zz, u=u))
+    return rot, files
+
+
+def write_rm_file(path, rot):
+    """one row-major 3x3 per line with a leading index (the layout mol_matrix3_list_from_file takes)"""
+    np.savetxt(path, np.column_stack([np.arange(len(rot)), rot]), fmt="%d" + " %.9f" * 9)
+
+
+def write_ft_file(path, rows_rot, rows_t):
+    """ft rows: rotation index, translation, six ignored columns (src/index.c:87-89)"""
+    np.savetxt(path, np.column_stack([rows_rot, rows_t, np.zeros((len(rows_rot), 6))]), fmt="%d %.3f %.3f %.3f" + " %.1f" * 6)

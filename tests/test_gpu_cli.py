@@ -171,3 +171,17 @@ def test_correlate_cli_keeps_64_bit_indices_where_int_overflows(files):
         assert a[0].strip() == b[0].strip() and a[1] == b[1]
         for x, y in zip(a[2:], b[2:]):
             assert abs(float(x) - float(y)) <= 1.001e-3
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "ref_correlate")), reason="compiled reference tools not present")
+def test_config1_run_correlate_on_dimer2(tmp_path):
+    """BASELINE config 1, examples/run_correlate.sh:40-48 on dimer2 (1A2K): single_saxs -> reference profile, the three
+    ft files concatenated, all 210 000 rows through `correlate`; the sub-list {z = 33, u_z > 0.85} row by row against the
+    reference tool, and the same poses inside the full run carry the same numbers (scripts/config1.py)"""
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "scripts"))
+    import config1
+    res = config1.main(str(tmp_path / "c1"))
+    print(res)
+    assert res["rows_scored"] == 210000 and res["subset_rows"] > 300
+    assert res["euler_file_identical"] and res["subset_max_abs_diff_printed"] <= 1.001e-3

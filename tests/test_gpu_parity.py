@@ -60,8 +60,9 @@ def test_expand_matches_reference(G, mol):
 
 
 def test_expand_ref_spf_golden(G):
-    """the reference's own test_pdb2spf (tests/saxs_test.c:59-127): rel 1e-3 against ref_spf on V and D;
-    W also depends on libmol2's SASA and is checked at 1e-3 of its scale (SASA)."""
+    """the reference's own test_pdb2spf (tests/saxs_test.c:59-127): rel 1e-3 against ref_spf on every V and D
+    coefficient; W (which also depends on libmol2's SASA routine, restated without its source) at the same relative
+    1e-3 on all but a counted set of small coefficients — see tests/test_cpu_host.py::test_mini_libmol2_pinned_by_ref_spf"""
     q, L = G["qvals"], int(G["L"])
     coef, rm, _ = capi.expand(MAP, G["rec_xyz"], names(G["rec_res"]), names(G["rec_atm"]), G["rec_radius"], q, L,
                               water_mode=2)
@@ -73,7 +74,12 @@ def test_expand_ref_spf_golden(G):
         nz = (np.abs(mine) > 0) & (np.abs(r) > 0)
         assert np.max(np.abs((r - mine)[nz] / r[nz])) < 1e-3
     w = ref[:, :, 4:6]
-    assert np.max(np.abs(coef[2] - w)) / np.abs(w).max() < 1e-3
+    scale = np.abs(w).max()
+    nz = (np.abs(coef[2]) > 0) & (np.abs(w) > 0)
+    bad = nz & (np.abs(coef[2] - w) > 1e-3 * np.abs(w))
+    print("W beyond 1e-3 relative: %d of %d coefficients" % (bad.sum(), nz.sum()))
+    assert bad.sum() <= 520 and np.abs(w[bad]).max() < 3e-4 * scale
+    assert np.max(np.abs(coef[2] - w)) < 1e-5 * scale
 
 
 def test_profile_from_spf(G):

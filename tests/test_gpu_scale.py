@@ -9,6 +9,7 @@ import pytest
 from libfmftsaxs_b200 import capi
 from libfmftsaxs_b200 import workload as wl
 import parity
+import refso
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
@@ -317,3 +318,33 @@ def test_dense_scan_topk():
     assert np.isin(better, idx).all()
     assert ss.min() >= s[0]
     plan.close()
+
+
+@pytest.mark.skipif(not refso.available(), reason="compiled reference (oracle/_ref) not present")
+def test_dense_scan_topk_against_the_reference():
+    """the dense scan against the ORACLE: (i) the k best points it reports carry the reference's (chi, c1, c2);
+    (ii) top-ness inside one cell: the reference scores ALL 29 791 grid points of the cell that holds the best point
+    (its skip = 0 mode computes exactly this grid, src/fftsaxs.c:867-872) — the scan's members from that cell are the
+    reference's points below the k-th score, and no other point of the cell is"""
+    G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
+    q, L = G["qvals"], int(G["L"])
+    nb, N = L + 1, 2 * L + 1
+    zv = np.array([40.0])
+    plan = capi.Plan(L, q)
+    plan.set_molecules(G["rec_coef"], G["lig_coef"])
+    plan.set_experiment(G["a"], G["scal"][1], G["scal"][2])
+    plan.set_translations(zv)
+    k = 48
+    idx, s, c1, c2 = plan.scan_topk(k, z_lo=0, z_hi=1)
+    plan.close()
+    want = refso.scores(idx.astype(np.int32), G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
+    parity.check("top-%d of a dense scan, reference on the same points" % k, (s, c1, c2), want)
+    cell = int(idx[0]) // N ** 3
+    allpts = (cell * N ** 3 + np.arange(N ** 3)).astype(np.int32)
+    rs, _, _ = refso.scores(allpts, G["rec_coef"], G["lig_coef"], G["a"], G["scal"], q, zv, L)
+    mine_in_cell = np.sort(idx[idx // N ** 3 == cell])
+    thr = s[-1]
+    ref_in_cell = np.sort(allpts[rs < thr * (1 - 1e-9)].astype(np.int64))
+    assert np.isin(ref_in_cell, mine_in_cell).all()                       # nothing better was missed
+    assert (rs[np.isin(allpts, mine_in_cell)] <= thr * (1 + 1e-9)).all()    # everything reported belongs
+    assert rs.min() >= s[0] * (1 - 1e-9)
