@@ -65,16 +65,12 @@ static __device__ __noinline__ double sxs_exp_out_of_range(double x) { return ex
 static inline double sxs_exp_out_of_range(double x) { return exp(x); }
 #endif
 
-/* tab: the SXS_EXP_TABLE_ENTRIES words of exp_table.h (shared memory on the device) */
-SXS_HD double sxs_exp_glibc(double x, const uint64_t *tab)
+/* The routine past its range test: valid for |x| < 512.  For |x| < 2^-54 (where the full routine returns 1 + x to keep
+ * the exception flags clean) it also returns 1.0: k = 0, r = x, and scale + scale * (x + ...) rounds to 1 — so a caller
+ * that knows |x| < 512 may call it for every argument and has no branch at all.
+ * tab: the SXS_EXP_TABLE_ENTRIES words of exp_table.h (shared memory on the device) */
+SXS_HD double sxs_exp_glibc_core(double x, const uint64_t *tab)
 {
-	const uint32_t abstop = (uint32_t)(SXS_EXP_BITS(x) >> 52) & 0x7ff;
-	if (abstop - 0x3c9u >= 0x3fu) {
-		if (abstop < 0x3c9u) {
-			return SXS_EXP_ADD(1.0, x); /* |x| < 2^-54, including +-0 */
-		}
-		return sxs_exp_out_of_range(x);
-	}
 	double kd = SXS_EXP_FMA(x, SXS_EXP_INVLN2N, SXS_EXP_SHIFT);
 	const uint64_t ki = SXS_EXP_BITS(kd);
 	kd = SXS_EXP_ADD(kd, -SXS_EXP_SHIFT);
@@ -92,6 +88,18 @@ SXS_HD double sxs_exp_glibc(double x, const uint64_t *tab)
 	const double tmp = SXS_EXP_FMA(r4, p45, s1);
 	const double scale = SXS_EXP_DBL(sbits);
 	return SXS_EXP_FMA(scale, tmp, scale);
+}
+
+SXS_HD double sxs_exp_glibc(double x, const uint64_t *tab)
+{
+	const uint32_t abstop = (uint32_t)(SXS_EXP_BITS(x) >> 52) & 0x7ff;
+	if (abstop - 0x3c9u >= 0x3fu) {
+		if (abstop < 0x3c9u) {
+			return SXS_EXP_ADD(1.0, x); /* |x| < 2^-54, including +-0 */
+		}
+		return sxs_exp_out_of_range(x);
+	}
+	return sxs_exp_glibc_core(x, tab);
 }
 
 #endif /* SXS_EXP_GLIBC_H */

@@ -119,18 +119,52 @@ SXS_HD void sxs_scale_begin(struct sxs_scale_run *r, const struct sxs_fit_ctx *c
 	r->down = 0.0;
 }
 
-SXS_HD void sxs_scale_node(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+/* a / d through r = RN(1 / d): two residual corrections with fused multiply-adds.  After the first, q is a faithful
+ * quotient (its error is below one ulp whatever the two roundings of a * r did); the second is then Markstein's
+ * correction step, which returns RN(a / d) exactly when r is the correctly rounded reciprocal (it is: the tables hold
+ * the IEEE quotient 1 / d).  Holds for a = 0 and for normal a, d, a / d (no overflow, no denormals) — the fit's
+ * (in - in_prev) / (q_i - q_{i-1}); tests/test_cpu_host.py checks it against the IEEE quotient on 10^8 operands.
+ * No branch, 5 instructions against ~13 + a slow-path test for the division nvcc emits. */
+SXS_HD double sxs_div_by_recip(double a, double d, double r)
+{
+	double q = SXS_EXP_MUL(a, r);
+	double e = SXS_EXP_FMA(-d, q, a);
+	q = SXS_EXP_FMA(e, r, q);
+	e = SXS_EXP_FMA(-d, q, a);
+	return SXS_EXP_FMA(e, r, q);
+}
+
+/* G(c1, q_i) = c1^3 exp(corr q_i^2) is the same number in both passes (and in begin() for node 0): the node steps take
+ * it as a parameter so that a caller may form it once.  recip: (in - in_prev) / dq[i] through sxs_div_by_recip. */
+SXS_HD void sxs_scale_begin_g(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, double c1, double c2,
+                              const struct sxs_six *x0, double G)
+{
+	r->corr = -ctx->mult * (c1 * c1 - 1.0);
+	r->in_prev = x0->vv - G * x0->vd + c2 * x0->vw + G * G * x0->dd - G * c2 * x0->dw + c2 * c2 * x0->ww;
+	r->c1_cube = c1 * c1 * c1;
+	r->c2 = c2;
+	r->q_prev = -1.0;
+	r->up = 0.0;
+	r->down = 0.0;
+}
+
+SXS_HD void sxs_scale_node_g(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x,
+                             double G, const int recip)
 {
 	const double *a = ctx->a;
 	const double c2 = r->c2;
 	const double q_cur = ctx->qvals[i];
-	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
 	const double in = x->vv - G * x->vd + c2 * x->vw + G * G * x->dd - G * c2 * x->dw + c2 * c2 * x->ww;
+	double tan;
+	if (recip) {
+		tan = sxs_div_by_recip(in - r->in_prev, ctx->dq[i], ctx->rq[i]);
+	} else {
 #if defined(__CUDA_ARCH__)
-	const double tan = (in - r->in_prev) / ctx->dq[i];
+		tan = (in - r->in_prev) / ctx->dq[i];
 #else
-	const double tan = (in - r->in_prev) / (ctx->dq ? ctx->dq[i] : q_cur - r->q_prev);
+		tan = (in - r->in_prev) / (ctx->dq ? ctx->dq[i] : q_cur - r->q_prev);
 #endif
+	}
 	const double buf = in - tan * q_cur;
 
 	r->up += buf * a[i * 6 + 1] + tan * a[i * 6 + 2];
@@ -138,6 +172,13 @@ SXS_HD void sxs_scale_node(struct sxs_scale_run *r, const struct sxs_fit_ctx *ct
 
 	r->in_prev = in;
 	r->q_prev = q_cur;
+}
+
+SXS_HD void sxs_scale_node(struct sxs_scale_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+{
+	const double q_cur = ctx->qvals[i];
+	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
+	sxs_scale_node_g(r, ctx, i, x, G, 0);
 }
 
 /* pass 2, src/min_saxs.c:3-105 with k frozen */
@@ -171,12 +212,11 @@ SXS_HD void sxs_grad_begin(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx
 	r->score = 0.0;
 }
 
-SXS_HD void sxs_grad_node(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+SXS_HD void sxs_grad_node_g(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x, double G)
 {
 	const double *a = ctx->a;
 	const double c2 = r->c2, k = r->k;
 	const double q_cur = ctx->qvals[i];
-	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
 	const double G_der = G * (r->three_over_c1 - r->two_c1_mult * q_cur * q_cur);
 
 	const double in = x->vv - G * x->vd + c2 * x->vw + G * G * x->dd - G * c2 * x->dw + c2 * c2 * x->ww;
@@ -215,6 +255,35 @@ SXS_HD void sxs_grad_node(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx,
 	r->q_prev = q_cur;
 }
 
+SXS_HD void sxs_grad_node(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, int i, const struct sxs_six *x)
+{
+	const double q_cur = ctx->qvals[i];
+	const double G = r->c1_cube * sxs_fit_exp(ctx, r->corr * q_cur * q_cur);
+	sxs_grad_node_g(r, ctx, i, x, G);
+}
+
+SXS_HD void sxs_grad_begin_g(struct sxs_grad_run *r, const struct sxs_fit_ctx *ctx, double c1, double c2, double k,
+                             const struct sxs_six *x0, double G)
+{
+	const double *q = ctx->qvals;
+	const double mult = ctx->mult;
+	r->corr = -mult * (c1 * c1 - 1.0);
+	r->three_over_c1 = 3.0 / c1;
+	r->two_c1_mult = 2.0 * c1 * mult;
+	const double G_der = G * (r->three_over_c1 - r->two_c1_mult * q[0] * q[0]);
+	r->in_prev = x0->vv - G * x0->vd + c2 * x0->vw + G * G * x0->dd - G * c2 * x0->dw + c2 * c2 * x0->ww;
+	r->in_der_c1_prev = -G_der * x0->vd + 2.0 * G * G_der * x0->dd - G_der * c2 * x0->dw;
+	r->in_der_c2_prev = x0->vw - G * x0->dw + 2.0 * c2 * x0->ww;
+	r->c1 = c1;
+	r->c1_cube = c1 * c1 * c1;
+	r->c2 = c2;
+	r->k = k;
+	r->q_prev = -1.0;
+	r->grad0 = 0.0;
+	r->grad1 = 0.0;
+	r->score = 0.0;
+}
+
 /* src/min_saxs.c:261-319 */
 SXS_HD double sxs_fit_best_scale(const struct sxs_fit_ctx *ctx, double c1, double c2)
 {
@@ -244,6 +313,41 @@ SXS_HD void sxs_fit_eval(const struct sxs_fit_ctx *ctx, double c1, double c2, do
 	*g0 = r.grad0;
 	*g1 = r.grad1;
 	*f = r.score;
+}
+
+/* The evaluation as the kernel's streamed objective performs it (sxs_exact.cu:fit_eval_fast): G formed once per node
+ * with the branch-free exp core and kept for pass 2 (stash[0 .. qnum-1]), the pass-1 quotient through the reciprocal
+ * table.  Same numbers as sxs_fit_eval bit for bit whenever |corr q^2| < 512 (the exp core's domain; the launcher
+ * checks the bound over the box of c1).  Needs ctx->rq, ctx->dq, ctx->etab. */
+SXS_HD void sxs_fit_eval_fast(const struct sxs_fit_ctx *ctx, double c1, double c2, double *stash, double *f, double *g0,
+                              double *g1)
+{
+	const double *q = ctx->qvals;
+	const double corr = -ctx->mult * (c1 * c1 - 1.0);
+	const double c1_cube = c1 * c1 * c1;
+	struct sxs_six x;
+	struct sxs_scale_run sr;
+	for (int i = 0; i < ctx->qnum; i++) {
+		const double G = c1_cube * sxs_exp_glibc_core(corr * q[i] * q[i], ctx->etab);
+		stash[i] = G;
+		SXS_LOAD6(ctx, i, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+		if (i == 0) {
+			sxs_scale_begin_g(&sr, ctx, c1, c2, &x, G);
+		}
+		sxs_scale_node_g(&sr, ctx, i, &x, G, 1);
+	}
+	const double k = sr.up / sr.down;
+	struct sxs_grad_run gr;
+	for (int i = 0; i < ctx->qnum; i++) {
+		SXS_LOAD6(ctx, i, x.vv, x.vd, x.vw, x.dd, x.dw, x.ww);
+		if (i == 0) {
+			sxs_grad_begin_g(&gr, ctx, c1, c2, k, &x, stash[0]);
+		}
+		sxs_grad_node_g(&gr, ctx, i, &x, stash[i]);
+	}
+	*g0 = gr.grad0;
+	*g1 = gr.grad1;
+	*f = gr.score;
 }
 
 /* One-pass form of the same objective.  The reference walks q twice per evaluation: once for the optimal scale

@@ -55,9 +55,20 @@ __shared__ double fs_q[SXS_FIT_MAXQ];       /* q grid */
 __shared__ double fs_rq[SXS_FIT_MAXQ];      /* 1 / (q_i - q_{i-1}) */
 __shared__ double fs_dq[SXS_FIT_MAXQ];      /* q_i - q_{i-1}, q_{-1} = -1 */
 __shared__ uint64_t fs_etab[SXS_EXP_TABLE_ENTRIES];
+__shared__ int fs_fast; /* |corr q^2| < 512 for every c1 of the box and every node: the exp core needs no range test */
 
-__device__ __forceinline__ void fit_tables_fill(const double *a, const double *qvals, int qnum)
+__device__ __forceinline__ void fit_tables_fill(const double *a, const double *qvals, int qnum, double mult)
 {
+	if (threadIdx.x == 0) {
+		/* |c1^2 - 1| <= max(1 - L1^2, U1^2 - 1) inside the box the optimiser never leaves */
+		const double span = fmax(1.0 - SXS_C1_LOWER * SXS_C1_LOWER, SXS_C1_UPPER * SXS_C1_UPPER - 1.0);
+		double qq = 0.0;
+		for (int i = 0; i < qnum; i++) {
+			qq = fmax(qq, qvals[i] * qvals[i]);
+		}
+		const double bound = fabs(mult) * span * qq;
+		fs_fast = (bound < 500.0) ? 1 : 0; /* false for NaN as well */
+	}
 	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
 		fs_etab[i] = d_exp_tab[i];
 	}
@@ -86,18 +97,35 @@ __device__ __forceinline__ void fit_store(const struct lq_state *st, double *__r
  *
  * The objective walks the point's row of 6*qnum cross terms twice (best scale, then f and gradient: the reference's
  * two passes, src/min_saxs.c:261-319 and :3-105).  The row is streamed from L2/HBM through a per-lane ring in shared
- * memory with 16-byte asynchronous copies (cp.async, three per node), SXS_FIT_RING nodes ahead of the arithmetic:
- * r2c ncu of the form with plain loads had 38 % of all stall samples on the two load sites (long scoreboard) at 8
- * warps per SM.
+ * memory with 16-byte asynchronous copies (cp.async, three per node), SXS_FIT_RING - 1 nodes ahead of the arithmetic.
+ * A node is straight-line code: exp through its core without the range test, the pass-1 quotient through the
+ * reciprocal table (both bit-exact, fit_eval.h) — 300 executed instructions per node and evaluation against 362 for
+ * the form with the two range branches (r2n / r2r ncu).
+ *
+ * Measured and not kept (profiles/r2_k4_notes.md, r2o-r2r): two or three nodes per trip (SXS_FIT_NPI; the fixed-latency
+ * "wait" share of the objective's stall samples falls from 45 % to 21 %, but the trip needs ~60 more registers inside a
+ * kernel that is at 255: its spills cost what the interleaving wins; variants/ builds of r2o-r2q), rows prefetched through registers instead of the
+ * ring (32 lanes = 32 cache lines per load: L1 thrashes), G(c1, q_i) kept in shared memory for pass 2 (one exp
+ * per node less, but 100 KB less L1 for the kernel's spills), the optimiser's matrices parked in shared memory
+ * across the objective, G of node i + 1 formed during node i.  Every one of them lands within 57-72 ms per 1.12 M fits
+ * against 55 for this form and 63 for the form before it.
  *
  * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) runs when NUM/DEN of the warp's waiting
- * lanes wait for it, so that it executes with most lanes active.  Tuning log: profiles/r2_k4_notes.md — including a
- * scheduled form (fits as slots of the block with their state in shared memory / an L2 scratch, warps as workers
- * on an objective queue and an iteration-boundary queue: 31.8 of 32 lanes in the objective) that ran at the same time
- * per fit with 6x the DRAM traffic and was not kept. */
+ * lanes wait for it, so that it executes with most lanes active. */
 #ifndef SXS_FIT_RING
 #define SXS_FIT_RING 4
 #endif
+
+struct fit_eval_args {
+	const double *row;
+	int qnum;
+	double mult, scale;
+};
+
+/* dynamic shared memory of k_fit: the lanes' row rings, SXS_FIT_RING slots of 48 bytes per lane; the slots of one ring
+ * position are lane-contiguous (48-byte lane stride: conflict-free 16-byte shared loads per quarter warp) */
+extern __shared__ __align__(16) double s_fit_dyn[];
+#define SXS_FIT_SLOT_BYTES (SXS_FIT_THREADS * 48)
 
 __device__ __forceinline__ void fit_cp16(unsigned dst_smem, const double *src)
 {
@@ -106,22 +134,8 @@ __device__ __forceinline__ void fit_cp16(unsigned dst_smem, const double *src)
 __device__ __forceinline__ void fit_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void fit_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-/* ring slot j of a lane: 48 bytes at shared address ring + j * SXS_FIT_SLOT_BYTES; the slots of one ring position are
- * lane-contiguous (48-byte lane stride: conflict-free 16-byte shared loads per quarter warp) */
-#define SXS_FIT_SLOT_BYTES (SXS_FIT_THREADS * 48)
-
-__device__ __forceinline__ void fit_issue(unsigned ring, int slot, const double *row, int node)
+__device__ __forceinline__ void fit_take(unsigned src, double scale, struct sxs_six *x)
 {
-	const unsigned dst = ring + (unsigned)slot * SXS_FIT_SLOT_BYTES;
-	const double *src = row + node * 6;
-	fit_cp16(dst, src);
-	fit_cp16(dst + 16, src + 2);
-	fit_cp16(dst + 32, src + 4);
-}
-
-__device__ __forceinline__ void fit_take(unsigned ring, int slot, double scale, struct sxs_six *x)
-{
-	const unsigned src = ring + (unsigned)slot * SXS_FIT_SLOT_BYTES;
 	double2 p0, p1, p2;
 	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p0.x), "=d"(p0.y) : "r"(src));
 	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p1.x), "=d"(p1.y) : "r"(src + 16));
@@ -131,39 +145,34 @@ __device__ __forceinline__ void fit_take(unsigned ring, int slot, double scale, 
 	x->dw = p2.x * scale; x->ww = p2.y * scale;
 }
 
-/* f, g of the fit at (c1, c2): sxs_fit_eval (fit_eval.h) with the row arriving through the ring.  The arithmetic is
- * that of sxs_scale_* / sxs_grad_* — node 0 is fed to begin() and to the first node() like the serial form.
+/* f, g of the fit at (c1, c2): sxs_fit_eval_fast (fit_eval.h) with the row arriving through the ring.
  *
- * The stream is the row twice (pass 1, pass 2); position s is requested SXS_FIT_RING - 1 positions ahead of its use.
- * The node loops are ROLLED on purpose: unrolled by the ring size (compile-time slots) the kernel grew to 10 500 SASS
- * instructions and ran 2.5x slower with 12 stall cycles per issue in "no instruction" (instruction-cache misses,
- * profiles/r2_k4_notes.md); ring slot and row pointer advance by pointer increments instead.
+ * The stream is the row twice (pass 1, pass 2); position s is requested SXS_FIT_RING - 1 positions ahead of its use
+ * (with one position of lead the wait for the copy was 26 % of the loop's stall samples, r2r ncu).  The node loops are
+ * ROLLED on purpose (unrolled by the ring size the kernel ran 2.5x slower on instruction-cache misses,
+ * profiles/r2_k4_notes.md); ring slot and row pointer advance by pointer increments.  Node 0 of each pass is peeled:
+ * it also seeds the running values (begin), and a test inside the loop would split the trip's straight-line code.
  *
- * SXS_FIT_EVAL_CALL: a real call (noinline) — the caller holds ~200 registers of optimiser state that are dead weight
- * in here; behind a call boundary the loops get a register allocation of their own. */
-struct fit_eval_args {
-	const double *row;
-	unsigned ring;
-	int qnum;
-	double mult, scale;
-};
-
+ * A real call (noinline): the caller holds ~150 registers of optimiser state that are dead weight in here; behind a
+ * call boundary the loops get a register allocation of their own. */
 #ifdef SXS_FIT_EVAL_INLINE
 #define SXS_FIT_EVAL_LINKAGE __device__ __forceinline__
 #else
 #define SXS_FIT_EVAL_LINKAGE __device__ __noinline__
 #endif
-
-SXS_FIT_EVAL_LINKAGE void fit_eval_streamed(const struct fit_eval_args *ap, double c1, double c2, double *out3)
+SXS_FIT_EVAL_LINKAGE void fit_eval_fast(const struct fit_eval_args *ap, double c1, double c2, double *out3)
 {
 	struct sxs_fit_ctx ctx;
 	ctx.x = ap->row; ctx.stride = 1; ctx.qstride = 6;
 	ctx.a = fs_a; ctx.qvals = fs_q; ctx.qnum = ap->qnum; ctx.mult = ap->mult; ctx.scale = ap->scale;
 	ctx.rq = fs_rq; ctx.dq = fs_dq; ctx.etab = fs_etab;
 	const double *row = ap->row;
-	const unsigned ring = ap->ring, ring_end = ap->ring + SXS_FIT_RING * SXS_FIT_SLOT_BYTES;
 	const double scale = ap->scale;
 	const int Q = ap->qnum;
+	const double corr = -ap->mult * (c1 * c1 - 1.0);
+	const double c1_cube = c1 * c1 * c1;
+	const unsigned ring = (unsigned)__cvta_generic_to_shared(s_fit_dyn) + threadIdx.x * 48u;
+	const unsigned ring_end = ring + SXS_FIT_RING * SXS_FIT_SLOT_BYTES;
 
 	/* positions 0 .. RING-2 */
 	{
@@ -171,7 +180,11 @@ SXS_FIT_EVAL_LINKAGE void fit_eval_streamed(const struct fit_eval_args *ap, doub
 #pragma unroll
 		for (int t = 0; t < SXS_FIT_RING - 1; t++) {
 			if (t < total) {
-				fit_issue(ring, t, row, t < Q ? t : t - Q);
+				const double *src = row + (t % Q) * 6;
+				const unsigned dst = ring + (unsigned)t * SXS_FIT_SLOT_BYTES;
+				fit_cp16(dst, src);
+				fit_cp16(dst + 16, src + 2);
+				fit_cp16(dst + 32, src + 4);
 			}
 			fit_cp_commit();
 		}
@@ -198,44 +211,64 @@ SXS_FIT_EVAL_LINKAGE void fit_eval_streamed(const struct fit_eval_args *ap, doub
 		nxt += SXS_FIT_SLOT_BYTES;                                             \
 		if (nxt == ring_end) nxt = ring;                                       \
 		fit_cp_wait<SXS_FIT_RING - 1>();                                       \
-		fit_take(cur, 0, scale, &x);                                           \
+		fit_take(cur, scale, &x);                                              \
 		cur += SXS_FIT_SLOT_BYTES;                                             \
 		if (cur == ring_end) cur = ring;                                       \
 	} while (0)
+#define SXS_FIT_G(i) (c1_cube * sxs_exp_glibc_core(corr * fs_q[i] * fs_q[i], fs_etab))
 
 	/* ---- pass 1: best scale ---- */
 	SXS_FIT_STEP();
-	sxs_scale_begin(&sr, &ctx, c1, c2, &x);
-	sxs_scale_node(&sr, &ctx, 0, &x);
+	{
+		const double G = SXS_FIT_G(0);
+		sxs_scale_begin_g(&sr, &ctx, c1, c2, &x, G);
+		sxs_scale_node_g(&sr, &ctx, 0, &x, G, 1);
+	}
 #pragma unroll 1
 	for (int i = 1; i < Q; i++) {
 		SXS_FIT_STEP();
-		sxs_scale_node(&sr, &ctx, i, &x);
+		sxs_scale_node_g(&sr, &ctx, i, &x, SXS_FIT_G(i), 1);
 	}
 	const double k = sr.up / sr.down;
 	/* ---- pass 2: f and gradient with k frozen ---- */
 	SXS_FIT_STEP();
-	sxs_grad_begin(&gr, &ctx, c1, c2, k, &x);
-	sxs_grad_node(&gr, &ctx, 0, &x);
+	{
+		const double G = SXS_FIT_G(0);
+		sxs_grad_begin_g(&gr, &ctx, c1, c2, k, &x, G);
+		sxs_grad_node_g(&gr, &ctx, 0, &x, G);
+	}
 #pragma unroll 1
 	for (int i = 1; i < Q; i++) {
 		SXS_FIT_STEP();
-		sxs_grad_node(&gr, &ctx, i, &x);
+		sxs_grad_node_g(&gr, &ctx, i, &x, SXS_FIT_G(i));
 	}
 #undef SXS_FIT_STEP
+#undef SXS_FIT_G
 	fit_cp_wait<0>();
 	out3[0] = gr.score;
 	out3[1] = gr.grad0;
 	out3[2] = gr.grad1;
 }
 
+/* The evaluation with the full exp (range test, libm beyond it) and IEEE quotients, plain loads: taken when
+ * |corr q^2| could reach 512 somewhere in the box of c1 (never with a physical q grid; fs_fast) */
+__device__ __noinline__ void fit_eval_safe(const struct fit_eval_args *ap, double c1, double c2, double *out3)
+{
+	struct sxs_fit_ctx ctx;
+	ctx.x = ap->row; ctx.stride = 1; ctx.qstride = 6;
+	ctx.a = fs_a; ctx.qvals = fs_q; ctx.qnum = ap->qnum; ctx.mult = ap->mult; ctx.scale = ap->scale;
+	ctx.rq = fs_rq; ctx.dq = fs_dq; ctx.etab = fs_etab;
+	sxs_fit_eval(&ctx, c1, c2, &out3[0], &out3[1], &out3[2]);
+}
+
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
-      int qnum, double mult, double peak, int rescale, double *__restrict__ res, unsigned long long *__restrict__ ticket)
+      int qnum, double mult, double peak, int rescale, double *__restrict__ res,
+      unsigned long long *__restrict__ ticket)
 {
-	extern __shared__ __align__(16) double s_ring[]; /* the lanes' row rings; the tables are static (fs_*) */
-	fit_tables_fill(a, qvals, qnum);
+	fit_tables_fill(a, qvals, qnum, mult);
 	__syncthreads();
+	const int fast = fs_fast;
 
 	struct lq_state st;
 	struct sxs_fit_ctx ctx;
@@ -243,10 +276,7 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 	ctx.qvals = fs_q; ctx.qnum = qnum; ctx.mult = mult;
 	ctx.x = X; ctx.scale = 1.0; ctx.rq = fs_rq; ctx.dq = fs_dq; ctx.etab = fs_etab;
 	struct fit_eval_args ea;
-	ea.ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 48u;
 	ea.qnum = qnum; ea.mult = mult; ea.scale = 1.0; ea.row = X;
-	const double sum_a0 = sxs_fit_sum_a0(fs_a, qnum);
-	(void)sum_a0;
 	long long p = -1;
 	bool drained = false;
 	/* what this lane's fit waits for */
@@ -301,14 +331,14 @@ k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a
 			continue;
 		}
 		if (mode == WANT_EVAL) {
-#ifdef SXS_FIT_EVAL_FUSED
-			sxs_fit_eval_fused(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
-#else
 			double fg[3];
 			ea.row = ctx.x; ea.scale = ctx.scale;
-			fit_eval_streamed(&ea, st.x[1], st.x[2], fg);
+			if (fast) {
+				fit_eval_fast(&ea, st.x[1], st.x[2], fg);
+			} else {
+				fit_eval_safe(&ea, st.x[1], st.x[2], fg);
+			}
 			st.f = fg[0]; st.g[1] = fg[1]; st.g[2] = fg[2];
-#endif
 			mode = EVALUATED;
 		}
 		__syncwarp();
@@ -328,6 +358,9 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	int dev = 0, sms = 148, per_sm = 4;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	/* dynamic shared memory: the lanes' row rings.  Kept small on purpose: the kernel's spills live in L1, which is what
+	 * shared memory leaves of 256 KB (with 219 KB of shared memory — G(c1, q) kept for pass 2 plus the optimiser's
+	 * matrices parked across the objective — the spill loads went to L2: 42 % of all stall samples, r2p ncu) */
 	const size_t shm = sizeof(double) * ((size_t)SXS_FIT_RING * SXS_FIT_THREADS * 6);
 	SXS_CK(cudaFuncSetAttribute(k_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit, SXS_FIT_THREADS, shm);

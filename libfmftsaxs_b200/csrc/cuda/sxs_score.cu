@@ -964,6 +964,46 @@ extern "C" int sxs_cuda_plan_set_translations(sxs_cuda_plan *p, const double *be
 
 /* ------------------------------------------------------------ score (core) */
 
+/* T-matrices of `zspan` z steps (d_zlist) and the translation of every flagged (z, b2) slab of the ligand table:
+ * K2b + K2c, two launches */
+static int launch_translate(sxs_cuda_plan *p, int zspan, const int *d_zlist, cudaStream_t st)
+{
+	const int L = p->L, Q = p->qnum, N = p->N, nb = p->nb;
+	k_tmatrix<<<grid_for((size_t)zspan * Q * nb * nb * nb, 256), 256, 0, st>>>(L, Q, zspan, d_zlist, p->d_dsymb, p->d_bessel, p->d_T);
+	SXS_CK_LAUNCH();
+	{
+		const int npair = (L + 2) / 2, rows = L + 2;
+		const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
+		const int GH = (N + 1) / 2;
+		int max_tiles = 0;
+		for (int ma = 0; ma < npair; ma++) {
+			const int mb = L - ma, nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
+			const int t = (nla + SXS_TR_ROWS - 1) / SXS_TR_ROWS + (nlb + SXS_TR_ROWS - 1) / SXS_TR_ROWS;
+			if (t > max_tiles) max_tiles = t;
+		}
+		const int threads_rt = 32 * ((max_tiles * GH + 31) / 32);
+		/* one output per thread: beyond L = 40 (the tiled form would need more than 512 threads), and for the
+		 * bit-identity test */
+		if (getenv("SXS_TRANSLATE_V1") != NULL || threads_rt > 512) {
+			int iters = (rows * N + 287) / 288;
+			int threads = 32 * ((rows * N + 32 * iters - 1) / (32 * iters));
+			if (threads > 288) threads = 288;
+			if (shm_t > 48 * 1024) {
+				SXS_CK(cudaFuncSetAttribute(k_translate_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+			}
+			k_translate_tiled<<<dim3(npair, 3 * Q, nb), threads, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		} else {
+			/* 4-row x 2-column tiles: (ceil(nla/4) + ceil(nlb/4)) * GH threads, nla + nlb = L + 2 */
+			if (shm_t > 48 * 1024) {
+				SXS_CK(cudaFuncSetAttribute(k_translate_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
+			}
+			k_translate_rt<<<dim3(npair, 3 * Q, nb), threads_rt, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
+		}
+	}
+	SXS_CK_LAUNCH();
+	return 0;
+}
+
 template <typename IndexT>
 static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, int z_lo, int z_hi, double *d_scores,
                       double *d_c1, double *d_c2, double *d_out3_sorted, double *d_cross_out, cudaStream_t st,
@@ -1143,37 +1183,11 @@ static int score_core(sxs_cuda_plan *p, const IndexT *d_index, long long nout, i
 		timer_begin(p, 1, st);
 		k_slab_flags<<<(unsigned)((g1 - g0 + 255) / 256), 256, 0, st>>>(p->d_pkeys, g0, g1, z_first, nb, per_zb2, p->d_slab_flag);
 		SXS_CK_LAUNCH(); launches++;
-		k_tmatrix<<<grid_for((size_t)zspan * Q * nb * nb * nb, 256), 256, 0, st>>>(L, Q, zspan, d_zlist, p->d_dsymb, p->d_bessel, p->d_T);
-		SXS_CK_LAUNCH(); launches++;
-		{
-			const int npair = (L + 2) / 2, rows = L + 2;
-			const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
-			const int GH = (N + 1) / 2;
-			int max_tiles = 0;
-			for (int ma = 0; ma < npair; ma++) {
-				const int mb = L - ma, nla = nb - ma, nlb = (mb != ma) ? nb - mb : 0;
-				const int t = (nla + SXS_TR_ROWS - 1) / SXS_TR_ROWS + (nlb + SXS_TR_ROWS - 1) / SXS_TR_ROWS;
-				if (t > max_tiles) max_tiles = t;
-			}
-			const int threads_rt = 32 * ((max_tiles * GH + 31) / 32);
-			/* one output per thread: beyond L = 40 (the tiled form would need more than 512 threads), and for the
-			 * bit-identity test */
-			if (getenv("SXS_TRANSLATE_V1") != NULL || threads_rt > 512) {
-				int iters = (rows * N + 287) / 288;
-				int threads = 32 * ((rows * N + 32 * iters - 1) / (32 * iters));
-				if (threads > 288) threads = 288;
-				if (shm_t > 48 * 1024) {
-					SXS_CK(cudaFuncSetAttribute(k_translate_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
-				}
-				k_translate_tiled<<<dim3(npair, 3 * Q, nb), threads, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
-			} else {
-				/* 4-row x 2-column tiles: (ceil(nla/4) + ceil(nlb/4)) * GH threads, nla + nlb = L + 2 */
-				if (shm_t > 48 * 1024) {
-					SXS_CK(cudaFuncSetAttribute(k_translate_rt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm_t));
-				}
-				k_translate_rt<<<dim3(npair, 3 * Q, nb), threads_rt, shm_t, st>>>(L, Q, zspan, p->d_slab_flag, p->d_T, p->d_Bt, p->d_St);
-			}
+		if (launch_translate(p, zspan, d_zlist, st) != 0) {
+			free(h_zlist);
+			return -1;
 		}
+		launches++;
 		SXS_CK_LAUNCH(); launches++;
 		timer_end(p, 1, st);
 		nslabs_total += (long long)zspan * nb;
@@ -1303,6 +1317,156 @@ extern "C" int sxs_cuda_plan_score_dev_i64(sxs_cuda_plan *p, const long long *d_
 	return score_core<long long>(p, d_index, nout, z_lo, z_hi, d_scores, d_c1, d_c2, NULL, NULL, (cudaStream_t)stream, NULL);
 }
 
+/* ------------------------------------------------------------ K3, dense form (every grid point of a cell)
+ * The list form above evaluates F at the poses a list names; a dense scan needs all N^3 points of a cell, and there the
+ * inner sums are shared: for a pair (g1, g2) the nine sums over l of one m serve all N values of a2.
+ *
+ *   C_k^m(g1, g2) = sum_{l >= m} At^c[m,l,g1] St^c'[m,l,g2]          (9 products -> 6 terms; 4 lanes split l, butterfly sum)
+ *   F_k(a2)       = Re sum_m fac_m w^(m a2) C_k^m                     (fac_0 = 1, fac_m = 2)
+ *                 = P(a2) - S(a2),  F_k(N - a2) = P(a2) + S(a2),  P = sum fac Re w^(m a2) Re C,  S = sum fac Im w^(m a2) Im C
+ *
+ * so the alpha transform costs half of a plain one-sided DFT.  Per cell and q that is 961 x ~7 900 DFMA = 15 MFLOP
+ * against 29 791 x 1 512 x 2 = 90 MFLOP for the list form with four a2 per thread (and 303 MFLOP point by point).
+ * The summation order differs from the list form, so the two agree to rounding, not to the bit.
+ *
+ * grid (pair tiles of TPB / LP, b2, q); LP (4 or 8) lanes per pair; lane j of a pair takes l = m + j, m + j + LP, ...
+ * and the a2 pairs {j + 1, j + 1 + LP, ...} of 1 .. (N-1)/2 (lane 0 also a2 = 0).
+ * X[sxs_x_index(b2 * N^3 + (a2 N + g1) N + g2, qnum, q, k)] = const_k[q] + 2 F_k. */
+/* LP lanes share a pair (they split l and a2), JMAX = a2 pairs per lane = ceil(L / LP): template parameters so that
+ * P, S stay in registers (with one L = 40 bound for every L the kernel spilled 992 bytes per thread and ran at the
+ * list form's speed).  TPB threads = TPB / LP pairs per block. */
+template <int LP, int SXS_DENSE_JMAX, int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At, const double2 *__restrict__ St,
+              const double2 *__restrict__ tw, const double *__restrict__ cst, double *__restrict__ X)
+{
+	extern __shared__ double2 s_tw[];
+	const int N = 2 * L + 1, ML = sxs_ml_count(L), NP = sxs_row_pad(N), H = (N - 1) / 2;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) {
+		s_tw[i] = tw[i];
+	}
+	__syncthreads();
+	const int b2 = blockIdx.y, q = blockIdx.z;
+	const int lane4 = threadIdx.x % LP;
+	const int pair = blockIdx.x * (TPB / LP) + (threadIdx.x / LP);
+	const bool live = pair < N * N;
+	const int g1 = live ? pair / N : 0, g2 = live ? pair % N : 0;
+	const size_t cstride = (size_t)ML * NP;
+	const double2 *a_ptr = At + (((size_t)b1 * qnum + q) * 3) * cstride + g1;
+	const double2 *s_ptr = St + (((size_t)(slab0 + b2) * qnum + q) * 3) * cstride + g2;
+
+	double P[SXS_DENSE_JMAX][6], S[SXS_DENSE_JMAX][6], F0[6];
+	int kk[SXS_DENSE_JMAX]; /* (m * a2) mod N for this lane's a2 values */
+#pragma unroll
+	for (int j = 0; j < SXS_DENSE_JMAX; j++) {
+		kk[j] = 0;
+#pragma unroll
+		for (int c = 0; c < 6; c++) {
+			P[j][c] = 0.0; S[j][c] = 0.0;
+		}
+	}
+#pragma unroll
+	for (int c = 0; c < 6; c++) {
+		F0[c] = 0.0;
+	}
+	int row0 = 0; /* packed index of (m, m) */
+	for (int m = 0; m <= L; m++) {
+		double2 C[6];
+#pragma unroll
+		for (int c = 0; c < 6; c++) {
+			C[c] = make_double2(0.0, 0.0);
+		}
+		for (int l = m + lane4; l <= L; l += LP) {
+			const size_t row = (size_t)(row0 + (l - m)) * NP;
+			const double2 av = __ldg(a_ptr + row), ad = __ldg(a_ptr + cstride + row), aw = __ldg(a_ptr + 2 * cstride + row);
+			const double2 sv = __ldg(s_ptr + row), sd = __ldg(s_ptr + cstride + row), sw = __ldg(s_ptr + 2 * cstride + row);
+			cmac(C[0], av, sv);
+			cmac(C[1], av, sd); cmac(C[1], ad, sv);
+			cmac(C[2], av, sw); cmac(C[2], aw, sv);
+			cmac(C[3], ad, sd);
+			cmac(C[4], ad, sw); cmac(C[4], aw, sd);
+			cmac(C[5], aw, sw);
+		}
+		row0 += L + 1 - m;
+#pragma unroll
+		for (int c = 0; c < 6; c++) {
+			C[c].x += __shfl_xor_sync(0xffffffffu, C[c].x, 1);
+			C[c].y += __shfl_xor_sync(0xffffffffu, C[c].y, 1);
+			C[c].x += __shfl_xor_sync(0xffffffffu, C[c].x, 2);
+			C[c].y += __shfl_xor_sync(0xffffffffu, C[c].y, 2);
+			if (LP == 8) {
+				C[c].x += __shfl_xor_sync(0xffffffffu, C[c].x, 4);
+				C[c].y += __shfl_xor_sync(0xffffffffu, C[c].y, 4);
+			}
+		}
+		const double fac = (m == 0) ? 1.0 : 2.0;
+		if (lane4 == 0) {
+#pragma unroll
+			for (int c = 0; c < 6; c++) {
+				F0[c] += fac * C[c].x;
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < SXS_DENSE_JMAX; j++) {
+			const int a2 = 1 + lane4 + LP * j;
+			if (a2 <= H) {
+				const double2 w = s_tw[kk[j]];
+				const double wx = fac * w.x, wy = fac * w.y;
+#pragma unroll
+				for (int c = 0; c < 6; c++) {
+					P[j][c] = fma(wx, C[c].x, P[j][c]);
+					S[j][c] = fma(wy, C[c].y, S[j][c]);
+				}
+				kk[j] += a2;
+				if (kk[j] >= N) {
+					kk[j] -= N;
+				}
+			}
+		}
+	}
+	if (!live) {
+		return;
+	}
+	double c6[6];
+#pragma unroll
+	for (int c = 0; c < 6; c++) {
+		c6[c] = cst[c * qnum + q];
+	}
+	const long long cell_base = (long long)b2 * N * N * N + (long long)g1 * N + g2;
+	if (lane4 == 0) {
+		double2 *xo = reinterpret_cast<double2 *>(X + sxs_x_index(cell_base, qnum, q, 0));
+		xo[0] = make_double2(c6[0] + 2.0 * F0[0], c6[1] + 2.0 * F0[1]);
+		xo[1] = make_double2(c6[2] + 2.0 * F0[2], c6[3] + 2.0 * F0[3]);
+		xo[2] = make_double2(c6[4] + 2.0 * F0[4], c6[5] + 2.0 * F0[5]);
+	}
+#pragma unroll
+	for (int j = 0; j < SXS_DENSE_JMAX; j++) {
+		const int a2 = 1 + lane4 + LP * j;
+		if (a2 <= H) {
+			double2 *xa = reinterpret_cast<double2 *>(X + sxs_x_index(cell_base + (long long)a2 * N * N, qnum, q, 0));
+			double2 *xb = reinterpret_cast<double2 *>(X + sxs_x_index(cell_base + (long long)(N - a2) * N * N, qnum, q, 0));
+			xa[0] = make_double2(c6[0] + 2.0 * (P[j][0] - S[j][0]), c6[1] + 2.0 * (P[j][1] - S[j][1]));
+			xa[1] = make_double2(c6[2] + 2.0 * (P[j][2] - S[j][2]), c6[3] + 2.0 * (P[j][3] - S[j][3]));
+			xa[2] = make_double2(c6[4] + 2.0 * (P[j][4] - S[j][4]), c6[5] + 2.0 * (P[j][5] - S[j][5]));
+			xb[0] = make_double2(c6[0] + 2.0 * (P[j][0] + S[j][0]), c6[1] + 2.0 * (P[j][1] + S[j][1]));
+			xb[1] = make_double2(c6[2] + 2.0 * (P[j][2] + S[j][2]), c6[3] + 2.0 * (P[j][3] + S[j][3]));
+			xb[2] = make_double2(c6[4] + 2.0 * (P[j][4] + S[j][4]), c6[5] + 2.0 * (P[j][5] + S[j][5]));
+		}
+	}
+}
+
+/* res[p*4 + 0..2] -> three arrays */
+__global__ void k_res_split(const double *__restrict__ res, long long n, double *__restrict__ s, double *__restrict__ c1,
+                            double *__restrict__ c2)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		s[i] = res[i * 4 + 0];
+		c1[i] = res[i * 4 + 1];
+		c2[i] = res[i * 4 + 2];
+	}
+}
+
 /* ------------------------------------------------------------ dense scan with top-k */
 
 __global__ void k_scan_indices(long long base, long long n, long long *__restrict__ idx)
@@ -1403,14 +1567,73 @@ extern "C" int sxs_cuda_plan_scan_topk(sxs_cuda_plan *p, int z_lo, int z_hi, int
 	long long launches = 0, points = 0;
 	if (e == cudaSuccess) {
 		rc = 0;
+		/* SXS_SCAN_LIST=1: every point goes through the list path (sort, distinct points, k_cross<4>) as in round 1 */
+		const int dense = getenv("SXS_SCAN_LIST") == NULL;
+		const int L = p->L, Q = p->qnum;
+		if (dense) {
+			const size_t slab_elems = (size_t)Q * 3 * sxs_ml_count(L) * sxs_row_pad((int)N);
+			if (ensure(&p->d_St, &p->cap_St, slab_elems * nb)) rc = -1;
+			if (rc == 0 && ensure(&p->d_T, &p->cap_T, (size_t)Q * nb * nb * nb)) rc = -1;
+			if (rc == 0 && ensure(&p->d_X, &p->cap_X, (size_t)per_row * 6 * Q)) rc = -1;
+			if (rc == 0 && ensure(&p->d_res, &p->cap_res, (size_t)per_row * 4)) rc = -1;
+			if (rc == 0 && (p->d_slab_flag == NULL || p->cap_slab < nb + 1)) {
+				if (p->d_slab_flag) cudaFree(p->d_slab_flag);
+				p->d_slab_flag = NULL;
+				if (cudaMalloc(&p->d_slab_flag, sizeof(int) * (nb + 1)) != cudaSuccess) rc = -1;
+				p->cap_slab = (int)nb + 1;
+			}
+		}
 		for (int z = z_lo; z < z_hi && rc == 0; z++) {
+			if (dense) {
+				/* every (z, b2) slab of this z is translated once and serves all b1 */
+				int *h_flag = (int *)malloc(sizeof(int) * (nb + 1));
+				for (int i = 0; i < nb; i++) h_flag[i] = 1;
+				h_flag[nb] = z;
+				e = cudaMemcpyAsync(p->d_slab_flag, h_flag, sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, st);
+				if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+				free(h_flag);
+				if (e != cudaSuccess) { rc = -1; break; }
+				timer_begin(p, 1, st);
+				rc = launch_translate(p, 1, p->d_slab_flag + nb, st);
+				timer_end(p, 1, st);
+				launches += 2;
+			}
 			for (int b1 = 0; b1 < nb && rc == 0; b1++) {
 				const long long base = ((long long)z * nb + b1) * per_row;
 				k_scan_indices<<<(unsigned)((per_row + 255) / 256), 256, 0, st>>>(base, per_row, d_idx);
-				rc = score_core<long long>(p, d_idx, per_row, z, z + 1, d_out, d_out + per_row, d_out + 2 * per_row, NULL,
-				                           NULL, st, NULL);
-				if (rc != 0) break;
-				launches += p->stats[2] + 4;
+				if (dense) {
+					timer_begin(p, 2, st);
+					{
+						const size_t sh = sizeof(double2) * N;
+						const unsigned npair = (unsigned)(N * N);
+#define SXS_DENSE_LAUNCH(LP, J, TPB, MINB)                                                                           \
+	k_cross_dense<LP, J, TPB, MINB><<<dim3((npair + (TPB / LP) - 1) / (TPB / LP), (unsigned)nb, (unsigned)Q), TPB, sh, st>>>( \
+	    L, Q, b1, 0, p->d_At, p->d_St, p->d_tw, p->d_const, p->d_X)
+						const int variant = getenv("SXS_DENSE_VARIANT") ? atoi(getenv("SXS_DENSE_VARIANT")) : 0; /* tuning */
+						if (L <= 8) SXS_DENSE_LAUNCH(4, 2, 256, 2);
+						else if (L <= 16 && variant == 1) SXS_DENSE_LAUNCH(4, 4, 256, 1);
+						else if (L <= 16 && variant == 2) SXS_DENSE_LAUNCH(8, 2, 256, 2);
+						else if (L <= 16 && variant == 3) SXS_DENSE_LAUNCH(8, 2, 256, 3);
+						else if (L <= 16) SXS_DENSE_LAUNCH(4, 4, 192, 2);
+						else if (L <= 32) SXS_DENSE_LAUNCH(8, 4, 192, 2);
+						else if (L <= 48) SXS_DENSE_LAUNCH(8, 6, 256, 1);
+						else { sxs_cuda_set_error("dense scan: L = %d beyond 48", L); rc = -1; break; }
+#undef SXS_DENSE_LAUNCH
+					}
+					if (cudaGetLastError() != cudaSuccess) { rc = -1; break; }
+					timer_end(p, 2, st);
+					timer_begin(p, 3, st);
+					rc = sxs_launch_fit(p->d_X, per_row, p->d_a, p->d_qvals, Q, p->mult, p->peak, 1, p->d_res, p->d_ticket, st);
+					timer_end(p, 3, st);
+					if (rc != 0) break;
+					k_res_split<<<(unsigned)((per_row + 255) / 256), 256, 0, st>>>(p->d_res, per_row, d_out, d_out + per_row, d_out + 2 * per_row);
+					launches += 4;
+				} else {
+					rc = score_core<long long>(p, d_idx, per_row, z, z + 1, d_out, d_out + per_row, d_out + 2 * per_row, NULL,
+					                           NULL, st, NULL);
+					if (rc != 0) break;
+					launches += p->stats[2] + 4;
+				}
 				points += per_row;
 				k_scan_keys<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_best3[cur], k, d_out, per_row, d_keys, d_vals);
 				e = cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys_sorted, d_vals, d_vals_sorted, (int)m, 0,

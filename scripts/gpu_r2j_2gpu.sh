@@ -1,0 +1,16 @@
+out=gpurun_out; mkdir -p $out
+nvidia-smi -L | head -4
+python -m pytest tests/test_gpu_scale.py -m gpu -q -rA -p no:cacheprovider -k "two_devices" > $out/r2j_pytest_2gpu.txt 2>&1; echo "rc=$?" >> $out/r2j_pytest_2gpu.txt
+grep -h "passed\|failed\|rc=\|rows," $out/r2j_pytest_2gpu.txt | cut -c1-250
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > $out/r2j_bench_strong_2gpu.json 2> $out/r2j_bench_strong_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 --scaling weak > $out/r2j_bench_weak_2gpu.json 2> $out/r2j_bench_weak_2gpu.err
+tail -3 $out/r2j_bench_strong_2gpu.err
+python - <<'PY'
+import json
+for f in ('r2j_bench_strong_2gpu','r2j_bench_weak_2gpu'):
+    try:
+        d=json.loads(open('gpurun_out/%s.json'%f).read().strip().split('\n')[-1])
+        print(f, d['scaling'], 'value %.4g e2e %.4g ms %.1f'%(d['value'],d['e2e']['value'],d['ms_per_step']), d.get('kernels_ms_per_step'), d['resident_equals_host_path'])
+    except Exception as e:
+        print(f,'ERR',e)
+PY

@@ -429,6 +429,35 @@ def test_exp_restatement_equals_host_libm(fit_host):
     assert fit_host.lib.cpu_exp_mismatches(ctypes.c_long(20_000_000)) == 0
 
 
+def test_fast_objective_pieces_are_exact(fit_host, G):
+    """the pieces the kernel's fast objective is built from (fit_eval.h): the exp core without its range test equals the
+    host libm on 12 M arguments with |x| < 500 including tiny and zero ones; the quotient through the reciprocal table
+    equals the IEEE quotient on 10^6 numerators per node spacing of three q grids (intensity-sized, tiny, zero, and
+    mantissas next to powers of two)"""
+    flags = open("/proc/cpuinfo").read()
+    if " fma " not in flags or " avx2 " not in flags:
+        pytest.skip("host libm does not select the FMA build of exp")
+    fit_host.lib.cpu_exp_core_mismatches.restype = ctypes.c_long
+    assert fit_host.lib.cpu_exp_core_mismatches(ctypes.c_long(12_000_000)) == 0
+    fit_host.lib.cpu_div_mismatches.restype = ctypes.c_long
+    for q in (np.ascontiguousarray(G["qvals"]), np.linspace(0.0, 0.5, 50), np.sort(np.random.default_rng(3).uniform(0, 0.6, 64))):
+        assert fit_host.lib.cpu_div_mismatches(refso.dptr(q), ctypes.c_int(len(q)), ctypes.c_long(1_000_000)) == 0
+
+
+def test_fast_objective_fits_bitwise_on_fixture(fit_host, G):
+    """the same 4052 fits with the evaluation in the kernel's fast form (sxs_fit_eval_fast): still the reference's
+    numbers bit for bit, evaluation counts included"""
+    FC = np.load(os.path.join(GOLD, "fit_cases.npz"))
+    X = np.ascontiguousarray(np.concatenate([FC["X52"], proto.perturbed_family(FC["X52"], 4000, 1)]))
+    want = np.concatenate([FC["fit52"], FC["fit_family"]])
+    q = np.ascontiguousarray(G["qvals"])
+    a = np.ascontiguousarray(G["a"])
+    got = np.zeros((len(X), 4))
+    fit_host.lib.cpu_fit_points_fast(refso.dptr(X), ctypes.c_int(len(X)), refso.dptr(a), refso.dptr(q), ctypes.c_int(len(q)),
+                                     ctypes.c_double(float(G["scal"][1])), ctypes.c_double(float(G["scal"][2])), refso.dptr(got))
+    assert np.array_equal(got, want)
+
+
 def test_fit_headers_bitwise_on_fixture(fit_host, G):
     """K4's optimiser + objective (the very headers the kernel includes), run on the host, against the stored
     outputs of the reference's L-BFGS-B: bit for bit, including the evaluation counts"""
