@@ -17,8 +17,10 @@
 
 #include <ctype.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 static void *xcalloc(size_t n, size_t sz)
 {
@@ -335,70 +337,31 @@ static int arc_cmp(const void *a, const void *b)
 	return (x > y) - (x < y);
 }
 
-/* Lee & Richards slice integration.  Atoms with zero radius neither receive
- * area nor occlude.  Slices are perpendicular to z, NZP = 1/P + 0.5 of them
- * per (expanded) sphere, sampled at slice mid-planes. */
-void accs(double *as, const struct mol_atom_group *ag, double r_solv, short cont_acc)
+/* The per-atom part of accs: atoms ir0 .. ir1-1 of the compact list.  Every atom's area depends on the read-only
+ * arrays only, so the atoms are split over host threads and the result does not depend on their number. */
+struct accs_job {
+	size_t ir0, ir1, n;
+	const double *x, *y, *z, *r, *rsq;
+	const double *lo;
+	const int *dim, *cell_start, *cell_items;
+	const size_t *ind;
+	double edge, r_solv;
+	short cont_acc;
+	double *as;
+};
+
+static void *accs_range(void *arg)
 {
+	const struct accs_job *jb = (const struct accs_job *)arg;
 	static const double P = 0.01;
 	const double pi = acos(-1.0);
 	const double pix2 = 2.0 * pi;
-	const size_t n_all = ag->natoms;
-
-	for (size_t i = 0; i < n_all; i++) {
-		as[i] = 0.0;
-	}
-
-	/* compact list of atoms with non-zero radius */
-	size_t n = 0;
-	size_t *ind = xcalloc(n_all, sizeof(size_t));
-	double rmax = 0.0;
-	for (size_t i = 0; i < n_all; i++) {
-		if (ag->vdw_radius[i] > 0.0) {
-			ind[n++] = i;
-			rmax = fmax(rmax, ag->vdw_radius[i] + r_solv);
-		}
-	}
-	if (n == 0) {
-		free(ind);
-		return;
-	}
-	double *x = xcalloc(n, sizeof(double)), *y = xcalloc(n, sizeof(double)), *z = xcalloc(n, sizeof(double));
-	double *r = xcalloc(n, sizeof(double)), *rsq = xcalloc(n, sizeof(double));
-	double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-	for (size_t k = 0; k < n; k++) {
-		const struct mol_vector3 *p = &ag->coords[ind[k]];
-		x[k] = p->X; y[k] = p->Y; z[k] = p->Z;
-		r[k] = ag->vdw_radius[ind[k]] + r_solv;
-		rsq[k] = r[k] * r[k];
-		lo[0] = fmin(lo[0], x[k]); hi[0] = fmax(hi[0], x[k]);
-		lo[1] = fmin(lo[1], y[k]); hi[1] = fmax(hi[1], y[k]);
-		lo[2] = fmin(lo[2], z[k]); hi[2] = fmax(hi[2], z[k]);
-	}
-
-	/* cubic cell list with edge 2*rmax: neighbours are in the 27 surrounding cells */
-	const double edge = 2.0 * rmax;
-	int dim[3];
-	for (int d = 0; d < 3; d++) {
-		dim[d] = (int)((hi[d] - lo[d]) / edge) + 1;
-	}
-	size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
-	int *cell_of = xcalloc(n, sizeof(int));
-	int *cell_start = xcalloc(ncell + 1, sizeof(int));
-	int *cell_items = xcalloc(n, sizeof(int));
-	for (size_t k = 0; k < n; k++) {
-		int cx = (int)((x[k] - lo[0]) / edge), cy = (int)((y[k] - lo[1]) / edge), cz = (int)((z[k] - lo[2]) / edge);
-		cell_of[k] = (cx * dim[1] + cy) * dim[2] + cz;
-		cell_start[cell_of[k] + 1]++;
-	}
-	for (size_t c = 0; c < ncell; c++) {
-		cell_start[c + 1] += cell_start[c];
-	}
-	int *fill = xcalloc(ncell, sizeof(int));
-	for (size_t k = 0; k < n; k++) {
-		cell_items[cell_start[cell_of[k]] + fill[cell_of[k]]++] = (int)k;
-	}
-	free(fill);
+	const double *x = jb->x, *y = jb->y, *z = jb->z, *r = jb->r, *rsq = jb->rsq, *lo = jb->lo;
+	const int *dim = jb->dim, *cell_start = jb->cell_start, *cell_items = jb->cell_items;
+	const size_t *ind = jb->ind;
+	const double edge = jb->edge, r_solv = jb->r_solv;
+	const short cont_acc = jb->cont_acc;
+	double *as = jb->as;
 
 	size_t nb_cap = 256;
 	int *nb = xcalloc(nb_cap, sizeof(int));
@@ -408,7 +371,7 @@ void accs(double *as, const struct mol_atom_group *ag, double r_solv, short cont
 
 	const int nzp = (int)(1.0 / P + 0.5);
 
-	for (size_t ir = 0; ir < n; ir++) {
+	for (size_t ir = jb->ir0; ir < jb->ir1; ir++) {
 		const double xr = x[ir], yr = y[ir], zr = z[ir], rr = r[ir], rrsq = rsq[ir];
 		const double rrx2 = 2.0 * rr;
 
@@ -534,6 +497,100 @@ void accs(double *as, const struct mol_atom_group *ag, double r_solv, short cont
 	}
 
 	free(arcs); free(nb); free(nb_d); free(nb_dsq); free(nb_dx); free(nb_dy);
+	return NULL;
+}
+
+/* Lee & Richards slice integration.  Atoms with zero radius neither receive
+ * area nor occlude.  Slices are perpendicular to z, NZP = 1/P + 0.5 of them
+ * per (expanded) sphere, sampled at slice mid-planes. */
+void accs(double *as, const struct mol_atom_group *ag, double r_solv, short cont_acc)
+{
+	const size_t n_all = ag->natoms;
+
+	for (size_t i = 0; i < n_all; i++) {
+		as[i] = 0.0;
+	}
+
+	/* compact list of atoms with non-zero radius */
+	size_t n = 0;
+	size_t *ind = xcalloc(n_all, sizeof(size_t));
+	double rmax = 0.0;
+	for (size_t i = 0; i < n_all; i++) {
+		if (ag->vdw_radius[i] > 0.0) {
+			ind[n++] = i;
+			rmax = fmax(rmax, ag->vdw_radius[i] + r_solv);
+		}
+	}
+	if (n == 0) {
+		free(ind);
+		return;
+	}
+	double *x = xcalloc(n, sizeof(double)), *y = xcalloc(n, sizeof(double)), *z = xcalloc(n, sizeof(double));
+	double *r = xcalloc(n, sizeof(double)), *rsq = xcalloc(n, sizeof(double));
+	double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+	for (size_t k = 0; k < n; k++) {
+		const struct mol_vector3 *p = &ag->coords[ind[k]];
+		x[k] = p->X; y[k] = p->Y; z[k] = p->Z;
+		r[k] = ag->vdw_radius[ind[k]] + r_solv;
+		rsq[k] = r[k] * r[k];
+		lo[0] = fmin(lo[0], x[k]); hi[0] = fmax(hi[0], x[k]);
+		lo[1] = fmin(lo[1], y[k]); hi[1] = fmax(hi[1], y[k]);
+		lo[2] = fmin(lo[2], z[k]); hi[2] = fmax(hi[2], z[k]);
+	}
+
+	/* cubic cell list with edge 2*rmax: neighbours are in the 27 surrounding cells */
+	const double edge = 2.0 * rmax;
+	int dim[3];
+	for (int d = 0; d < 3; d++) {
+		dim[d] = (int)((hi[d] - lo[d]) / edge) + 1;
+	}
+	size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+	int *cell_of = xcalloc(n, sizeof(int));
+	int *cell_start = xcalloc(ncell + 1, sizeof(int));
+	int *cell_items = xcalloc(n, sizeof(int));
+	for (size_t k = 0; k < n; k++) {
+		int cx = (int)((x[k] - lo[0]) / edge), cy = (int)((y[k] - lo[1]) / edge), cz = (int)((z[k] - lo[2]) / edge);
+		cell_of[k] = (cx * dim[1] + cy) * dim[2] + cz;
+		cell_start[cell_of[k] + 1]++;
+	}
+	for (size_t c = 0; c < ncell; c++) {
+		cell_start[c + 1] += cell_start[c];
+	}
+	int *fill = xcalloc(ncell, sizeof(int));
+	for (size_t k = 0; k < n; k++) {
+		cell_items[cell_start[cell_of[k]] + fill[cell_of[k]]++] = (int)k;
+	}
+	free(fill);
+
+	/* host threads: SXS_HOST_THREADS, else the online processors, at least 64 atoms per thread */
+	int nthreads = getenv("SXS_HOST_THREADS") ? atoi(getenv("SXS_HOST_THREADS")) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (nthreads > 64) nthreads = 64;
+	if ((size_t)nthreads > n / 64 + 1) nthreads = (int)(n / 64 + 1);
+	if (nthreads < 1) nthreads = 1;
+	struct accs_job jobs[64];
+	pthread_t th[64];
+	for (int k = 0; k < nthreads; k++) {
+		struct accs_job *jb = &jobs[k];
+		jb->ir0 = n * (size_t)k / (size_t)nthreads; jb->ir1 = n * (size_t)(k + 1) / (size_t)nthreads; jb->n = n;
+		jb->x = x; jb->y = y; jb->z = z; jb->r = r; jb->rsq = rsq; jb->lo = lo; jb->dim = dim;
+		jb->cell_start = cell_start; jb->cell_items = cell_items; jb->ind = ind;
+		jb->edge = edge; jb->r_solv = r_solv; jb->cont_acc = cont_acc; jb->as = as;
+	}
+	int started = 0;
+	for (int k = 1; k < nthreads; k++) {
+		if (pthread_create(&th[k], NULL, accs_range, &jobs[k]) != 0) {
+			break;
+		}
+		started = k;
+	}
+	accs_range(&jobs[0]);
+	for (int k = started + 1; k < nthreads; k++) {
+		accs_range(&jobs[k]); /* a thread that could not be created: its atoms here */
+	}
+	for (int k = 1; k <= started; k++) {
+		pthread_join(th[k], NULL);
+	}
+
 	free(cell_of); free(cell_start); free(cell_items);
 	free(x); free(y); free(z); free(r); free(rsq); free(ind);
 }

@@ -8,6 +8,9 @@
  * Where the reference spreads z steps over MPI ranks, this program is one process: the library shards
  * the z steps over the visible B200s (SXS_CUDA_DEVICES).
  */
+#define _POSIX_C_SOURCE 200809L
+#include <time.h>
+
 #include "common.h"
 
 #include "fftsaxs.h"
@@ -17,6 +20,23 @@
 #include "mol2/pdb.h"
 #include "mol2/prms.h"
 #include "mol2/vector.h"
+
+/* SXS_TIMING=1: wall time of every phase on stdout (the reference prints one CPU-clock total only) */
+static double wall_now(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static double g_phase_t0;
+static void phase_done(const char *name)
+{
+	const double t = wall_now();
+	if (getenv("SXS_TIMING") != NULL) {
+		printf("[phase] %-28s %.3f s\n", name, t - g_phase_t0);
+	}
+	g_phase_t0 = t;
+}
 
 static void usage(void)
 {
@@ -62,6 +82,7 @@ int main(int argc, char *argv[])
 	}
 
 	const clock_t t0 = clock();
+	g_phase_t0 = wall_now();
 	const int qnum = QNUM;
 	double *qvals = sxs_mkarray(0.0, QMAX, qnum);
 
@@ -73,6 +94,7 @@ int main(int argc, char *argv[])
 	SXS_PRINTF("Reading form-factors ...\n");
 	struct saxs_form_factor_table *ff = default_ff_table(map_path);
 
+	phase_done("parameter files");
 	SXS_PRINTF("Reading receptor ...\n");
 	struct mol_vector3 coe, com;
 	struct mol_atom_group *rec = load_centred(rec_path, prms, 1, &coe);
@@ -81,6 +103,7 @@ int main(int argc, char *argv[])
 	struct mol_atom_group *lig = load_centred(lig_path, prms, 0, &com);
 	struct sxs_spf_full *B = atom_grp2spf(lig, ff, qvals, qnum, L, 1);
 
+	phase_done("PDB + SASA + expansion (K1)");
 	/* ligand centre relative to the receptor centre in the input frames (tools/correlate.c:108-113) */
 	struct mol_vector3 ref_lig;
 	MOL_VEC_SUB(ref_lig, com, coe);
@@ -96,6 +119,7 @@ int main(int argc, char *argv[])
 		sxs_ft_file2euler_file(eul_path, ft_path, rm_path, &ref_lig);
 	}
 
+	phase_done("ft + rm -> Euler file + indices");
 	SXS_PRINTF("Reading experiment ...\n");
 	struct sxs_profile *exp_profile = sxs_profile_read(exp_path);
 	if (exp_profile == NULL) {
@@ -163,6 +187,7 @@ int main(int argc, char *argv[])
 		fclose(ef);
 	}
 
+	phase_done("experiment + index arrays");
 	double *score = (double *)calloc(n ? n : 1, sizeof(double));
 	double *c1 = (double *)calloc(n ? n : 1, sizeof(double));
 	double *c2 = (double *)calloc(n ? n : 1, sizeof(double));
@@ -173,9 +198,11 @@ int main(int argc, char *argv[])
 		sxs_compute_saxs_scores(score, c1, c2, index, (int)n, A, B, params, qvals, qnum, zvals, znum, L, 1);
 	}
 
+	phase_done("scoring (K2-K4 + copies)");
 	printf("\nTime passed: %.3f\n", (double)(clock() - t0) / CLOCKS_PER_SEC);
 	printf("Writing results to %s\n", out_path);
 	sxs_write_score_rows(out_path, (long long)n, order, ft_id, score, c1, c2, 0);
+	phase_done("output rows");
 	printf("\nCorrelation finished\n");
 
 	free(score); free(c1); free(c2); free(index); free(index64); free(ft_id); free(order);

@@ -49,13 +49,14 @@ def main():
            os.path.join(d, "lig.pdb"), os.path.join(d, "exp.dat"), "15", os.path.join(d, "euler.out"), os.path.join(d, "scores.out")]
     for rep in range(2):
         t0 = time.time()
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, SXS_TIMING="1"))
         dt = time.time() - t0
         assert r.returncode == 0, r.stdout[-2000:]
         rows = sum(1 for _ in open(os.path.join(d, "scores.out")))
         cpu = [l for l in r.stdout.splitlines() if l.startswith("Time passed")]
         print("run %d: correlate wall %.2f s, %d scored rows, %.0f rows/s end to end; %s (CPU clock of the tool)" %
               (rep, dt, rows, rows / dt, cpu[-1] if cpu else ""), flush=True)
+        print("\n".join(l for l in r.stdout.splitlines() if l.startswith("[phase]")), flush=True)
     for f in ("ft.000", "euler.out", "scores.out"):
         os.remove(os.path.join(d, f))
 
