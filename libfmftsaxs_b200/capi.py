@@ -110,6 +110,23 @@ def cuda_exp(x, device=0):
     return y
 
 
+def cuda_ft_rows_to_indices(rot_id, trans, rots, ref_lig, zvals, L, device=0):
+    """ft rows -> flat 64-bit grid indices on the device (sxs_cuda_ft_rows_to_indices): -1 = z not on the table,
+    -2 = rotation id outside the table.  rots: (nrot, 9) row-major matrices."""
+    rot_id = np.ascontiguousarray(rot_id, dtype=np.int32)
+    trans = _c(np.asarray(trans, dtype=np.float64).reshape(-1, 3))
+    rots = _c(np.asarray(rots, dtype=np.float64).reshape(-1, 9))
+    ref_lig = _c(np.asarray(ref_lig, dtype=np.float64).reshape(3))
+    zvals = _c(zvals)
+    out = np.zeros(len(rot_id), dtype=np.int64)
+    f = lib().sxs_cuda_ft_rows_to_indices
+    f.argtypes = [C.c_int, _ip, _dp, C.c_longlong, _dp, C.c_longlong, _dp, _dp, C.c_int, C.c_int, _llp]
+    f.restype = C.c_int
+    _check(f(device, rot_id.ctypes.data_as(_ip), dptr(trans), len(rot_id), dptr(rots), len(rots), dptr(ref_lig), dptr(zvals),
+             len(zvals), int(L), out.ctypes.data_as(_llp)), "sxs_cuda_ft_rows_to_indices")
+    return out
+
+
 # ------------------------------------------------------------------ reference-shaped API (flat adapters)
 
 def mkarray(begin, end, n):

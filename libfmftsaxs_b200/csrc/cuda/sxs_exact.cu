@@ -491,6 +491,151 @@ extern "C" int sxs_cuda_exp_array(int device, const double *x, long long n, doub
 	return 0;
 }
 
+/* ------------------------------------------------------------------ ft rows -> grid indices
+ * One thread per ft row: (rotation id, translation) -> (z, b1, g1, a2, b2, g2) as sxs_ft2euler does it
+ * (src/index.c:38-75), every value through the three decimals of the Euler text file (src/index.c:114 writes "% .3f",
+ * tools/correlate.c:214 reads it back), the z table lookup and the snapping of tools/correlate.c:219-247 /
+ * sxs_euler_to_index64.  In this translation unit because the products of the rotation composition must not be fused
+ * (-fmad=false, like the host's -ffp-contract=off).
+ *
+ * The text round trip is arithmetic here: the decimal the C library prints is the integer nearest to x * 1000 taken
+ * exactly (ties to even), and what strtod makes of it is the IEEE quotient n / 1000.  x * 1000 = p + e exactly with
+ * p = RN(x * 1000), e = fma(x, 1000, -p); only when p lies exactly on k + 1/2 does e decide.
+ * acos / sin / cos are CUDA's (<= 1-2 ulp from the host libm's): an angle can differ from the host's before the
+ * rounding only in its last bits, i.e. after it only within ~1e-13 of a rounding boundary of the third decimal. */
+__device__ __forceinline__ double ft_through_text(double x)
+{
+	const double p = x * 1000.0;
+	const double e = fma(x, 1000.0, -p);
+	double n = rint(p);
+	const double diff = p - n;
+	if (diff == 0.5 && e > 0.0) {
+		n += 1.0;
+	} else if (diff == -0.5 && e < 0.0) {
+		n -= 1.0;
+	}
+	return n / 1000.0;
+}
+
+__device__ __forceinline__ double ft_clamp_unit(double a) { return a < -1.0 ? -1.0 : (a > 1.0 ? 1.0 : a); }
+
+#define SXS_FT_PI 3.14159265358979323846
+
+__global__ void k_ft_rows_to_index(const int *__restrict__ rot_id, const double *__restrict__ trans, long long n,
+                                   const double *__restrict__ rots, long long nrot, double rx, double ry, double rz,
+                                   const double *__restrict__ zvals, int znum, int L, long long *__restrict__ out)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) {
+		return;
+	}
+	const int id = rot_id[i];
+	if (id < 0 || id >= nrot) {
+		out[i] = -2; /* rotation index outside the rotation table */
+		return;
+	}
+	const double vx = trans[3 * i] + rx, vy = trans[3 * i + 1] + ry, vz = trans[3 * i + 2] + rz;
+	double z = round(sqrt(vx * vx + vy * vy + vz * vz));
+	double b1 = acos(ft_clamp_unit(vz / z));
+	double g1 = acos(ft_clamp_unit(-vx / (z * sin(b1))));
+	if (vy / (z * sin(b1)) < 0.0) {
+		g1 = 2 * SXS_FT_PI - g1;
+	}
+	/* active z-y-z rotation (0, b1, g1), src/saxs_utils.c:65-79 with alpha = 0 spelled out as the host evaluates it */
+	const double ca = cos(0.0), sa = sin(0.0);
+	const double cb = cos(b1), sb = sin(b1);
+	const double cg = cos(g1), sg = sin(g1);
+	double a[9];
+	a[0] = cg * cb * ca - sg * sa;  a[1] = -sg * cb * ca - cg * sa; a[2] = sb * ca;
+	a[3] = cg * cb * sa + sg * ca;  a[4] = -sg * cb * sa + cg * ca; a[5] = sb * sa;
+	a[6] = -cg * sb;                a[7] = sg * sb;                 a[8] = cb;
+	const double *b = rots + 9 * (long long)id;
+	/* the entries of (rec_rm x rm) the angles need: m13, m23, m31, m32, m33 (src/saxs_utils.c:81-94) */
+	const double m13 = a[0] * b[2] + a[1] * b[5] + a[2] * b[8];
+	const double m23 = a[3] * b[2] + a[4] * b[5] + a[5] * b[8];
+	const double m31 = a[6] * b[0] + a[7] * b[3] + a[8] * b[6];
+	const double m32 = a[6] * b[1] + a[7] * b[4] + a[8] * b[7];
+	const double m33 = a[6] * b[2] + a[7] * b[5] + a[8] * b[8];
+	double b2 = acos(ft_clamp_unit(m33));
+	double a2 = acos(ft_clamp_unit(m13 / sin(b2)));
+	if (m23 / sin(b2) < 0.0) {
+		a2 = 2 * SXS_FT_PI - a2;
+	}
+	double g2 = acos(ft_clamp_unit(-m31 / sin(b2)));
+	if (m32 / sin(b2) < 0.0) {
+		g2 = 2 * SXS_FT_PI - g2;
+	}
+	z = ft_through_text(z); b1 = ft_through_text(b1); g1 = ft_through_text(g1);
+	a2 = ft_through_text(a2); b2 = ft_through_text(b2); g2 = ft_through_text(g2);
+	/* a translation on the z axis or a ligand z axis on the receptor's gives 0 / 0 above: "nan" in the Euler file, and
+	 * (int)round(nan) = INT_MIN in the tool's index (tools/correlate.c:225-240), a negative index that the host route
+	 * drops (index_rows.c keeps rows with flat >= 0); the same rows are dropped here */
+	if (b1 != b1 || g1 != g1 || a2 != a2 || b2 != b2 || g2 != g2 || z != z) {
+		out[i] = -1;
+		return;
+	}
+	long long flat = -1;
+	for (int k = 0; k < znum; k++) {
+		if (zvals[k] > z - 0.001 && zvals[k] < z + 0.001) {
+			const long long nbeta = L + 1, nn = 2 * L + 1;
+			const double b_step = SXS_FT_PI / L;
+			const double a_step = 2.0 * SXS_FT_PI / nn;
+			const double a2r = 2 * SXS_FT_PI - a2;
+			const double g2r = 2 * SXS_FT_PI - g2;
+			long long f = k * nbeta;
+			f = (f + (int)(round(b1 / b_step))) * nbeta;
+			f = (f + (int)(round(b2 / b_step))) * nn;
+			f = (f + (int)(round(a2r / a_step))) * nn;
+			f = (f + (int)(round(g1 / a_step))) * nn;
+			f = f + (int)(round(g2r / a_step));
+			flat = f;
+			break; /* the 1 A table of the tool matches at most one z */
+		}
+	}
+	out[i] = flat;
+}
+
+extern "C" int sxs_cuda_ft_rows_to_indices_dev(const int *d_rot_id, const double *d_trans, long long n, const double *d_rots,
+                                               long long nrot, const double *ref_lig, const double *d_zvals, int znum, int L,
+                                               long long *d_index, void *stream)
+{
+	if (n <= 0) {
+		return 0;
+	}
+	k_ft_rows_to_index<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_rot_id, d_trans, n, d_rots, nrot, ref_lig[0],
+	                                                                                  ref_lig[1], ref_lig[2], d_zvals, znum, L, d_index);
+	SXS_CK_LAUNCH();
+	return 0;
+}
+
+extern "C" int sxs_cuda_ft_rows_to_indices(int device, const int *rot_id, const double *trans, long long n, const double *rots,
+                                           long long nrot, const double *ref_lig, const double *zvals, int znum, int L,
+                                           long long *index)
+{
+	if (n <= 0) {
+		return 0;
+	}
+	SXS_CK(cudaSetDevice(device));
+	int *d_id = NULL;
+	double *d_t = NULL, *d_r = NULL, *d_z = NULL;
+	long long *d_o = NULL;
+	SXS_CK(cudaMalloc(&d_id, sizeof(int) * n));
+	SXS_CK(cudaMalloc(&d_t, sizeof(double) * 3 * n));
+	SXS_CK(cudaMalloc(&d_r, sizeof(double) * 9 * nrot));
+	SXS_CK(cudaMalloc(&d_z, sizeof(double) * znum));
+	SXS_CK(cudaMalloc(&d_o, sizeof(long long) * n));
+	SXS_CK(cudaMemcpy(d_id, rot_id, sizeof(int) * n, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_t, trans, sizeof(double) * 3 * n, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_r, rots, sizeof(double) * 9 * nrot, cudaMemcpyHostToDevice));
+	SXS_CK(cudaMemcpy(d_z, zvals, sizeof(double) * znum, cudaMemcpyHostToDevice));
+	int rc = sxs_cuda_ft_rows_to_indices_dev(d_id, d_t, n, d_r, nrot, ref_lig, d_z, znum, L, d_o, NULL);
+	if (rc == 0) {
+		SXS_CK(cudaMemcpy(index, d_o, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+	}
+	cudaFree(d_id); cudaFree(d_t); cudaFree(d_r); cudaFree(d_z); cudaFree(d_o);
+	return rc;
+}
+
 /* ------------------------------------------------------------------ self terms */
 
 /* one thread per (k, q); serial over (l, m) in the reference's order */

@@ -1340,20 +1340,52 @@ __global__ void __launch_bounds__(TPB, MINB)
 k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At, const double2 *__restrict__ St,
               const double2 *__restrict__ tw, const double *__restrict__ cst, double *__restrict__ X)
 {
-	extern __shared__ double2 s_tw[];
+	/* shared memory: twiddles [N] | two stages of { S rows of one m: [3][L + 1][NP], A entries of one m: [3][L + 1][GA] }.
+	 * The operands of m + 1 are copied (cp.async, whole 16-byte elements, coalesced rows) while m is computed: with
+	 * the lanes loading them straight from global memory half of all stall samples sat on the long scoreboard and the
+	 * L1 pipe was 74 % busy (r2v ncu, 47 ms per z); each S row is now fetched once per block instead of once per lane. */
+	extern __shared__ double2 s_dense[];
 	const int N = 2 * L + 1, ML = sxs_ml_count(L), NP = sxs_row_pad(N), H = (N - 1) / 2;
+	const int GA = (TPB / LP + N - 1) / N + 1; /* g1 values the block's TPB / LP consecutive pairs can span */
+	const int nlmax = L + 1;
+	double2 *s_tw = s_dense;
+	const int stage_elems = 3 * nlmax * NP + 3 * nlmax * GA;
+	double2 *stage0 = s_dense + ((N + 1) & ~1);
 	for (int i = threadIdx.x; i < N; i += blockDim.x) {
 		s_tw[i] = tw[i];
 	}
-	__syncthreads();
 	const int b2 = blockIdx.y, q = blockIdx.z;
 	const int lane4 = threadIdx.x % LP;
-	const int pair = blockIdx.x * (TPB / LP) + (threadIdx.x / LP);
+	const int pair0 = blockIdx.x * (TPB / LP);
+	const int pair = pair0 + (threadIdx.x / LP);
 	const bool live = pair < N * N;
-	const int g1 = live ? pair / N : 0, g2 = live ? pair % N : 0;
+	const int g1base = min(pair0 / N, N - 1);
+	const int g1 = live ? pair / N : g1base, g2 = live ? pair % N : 0;
+	const int ga = g1 - g1base; /* 0 .. GA-1 */
 	const size_t cstride = (size_t)ML * NP;
-	const double2 *a_ptr = At + (((size_t)b1 * qnum + q) * 3) * cstride + g1;
-	const double2 *s_ptr = St + (((size_t)(slab0 + b2) * qnum + q) * 3) * cstride + g2;
+	const double2 *a_base = At + (((size_t)b1 * qnum + q) * 3) * cstride;
+	const double2 *s_base = St + (((size_t)(slab0 + b2) * qnum + q) * 3) * cstride;
+
+	/* copy of the operands of one m into a stage: S rows row0 .. row0 + nl - 1 (contiguous, NP elements each, padding
+	 * included) of the three components, and the A entries g1base .. g1base + GA - 1 of the same rows */
+	auto stage_fill = [&](double2 *stg, int m, int row0) {
+		const int nl = L + 1 - m;
+		const int s_cnt = nl * NP;
+		for (int i = threadIdx.x; i < 3 * s_cnt; i += TPB) {
+			const int c = i / s_cnt, r = i - c * s_cnt;
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + c * nlmax * NP + r);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_base + c * cstride + (size_t)row0 * NP + r) : "memory");
+		}
+		const int a_cnt = nl * GA;
+		for (int i = threadIdx.x; i < 3 * a_cnt; i += TPB) {
+			const int c = i / a_cnt, r = i - c * a_cnt;
+			const int rl = r / GA, gi = r - rl * GA;
+			const int gg = min(g1base + gi, NP - 1);
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + 3 * nlmax * NP + c * nlmax * GA + r);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a_base + c * cstride + (size_t)(row0 + rl) * NP + gg) : "memory");
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
 
 	double P[SXS_DENSE_JMAX][6], S[SXS_DENSE_JMAX][6], F0[6];
 	int kk[SXS_DENSE_JMAX]; /* (m * a2) mod N for this lane's a2 values */
@@ -1370,16 +1402,23 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 		F0[c] = 0.0;
 	}
 	int row0 = 0; /* packed index of (m, m) */
+	stage_fill(stage0, 0, 0);
 	for (int m = 0; m <= L; m++) {
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads(); /* the copies of m have landed for every thread, and everybody is done with m - 1 */
+		const double2 *stg = stage0 + (m & 1) * stage_elems;
+		if (m < L) {
+			stage_fill(stage0 + ((m + 1) & 1) * stage_elems, m + 1, row0 + L + 1 - m);
+		}
+		const double2 *sS = stg + g2, *sA = stg + 3 * nlmax * NP + ga;
 		double2 C[6];
 #pragma unroll
 		for (int c = 0; c < 6; c++) {
 			C[c] = make_double2(0.0, 0.0);
 		}
-		for (int l = m + lane4; l <= L; l += LP) {
-			const size_t row = (size_t)(row0 + (l - m)) * NP;
-			const double2 av = __ldg(a_ptr + row), ad = __ldg(a_ptr + cstride + row), aw = __ldg(a_ptr + 2 * cstride + row);
-			const double2 sv = __ldg(s_ptr + row), sd = __ldg(s_ptr + cstride + row), sw = __ldg(s_ptr + 2 * cstride + row);
+		for (int r = lane4; r <= L - m; r += LP) {
+			const double2 av = sA[r * GA], ad = sA[nlmax * GA + r * GA], aw = sA[2 * nlmax * GA + r * GA];
+			const double2 sv = sS[r * NP], sd = sS[nlmax * NP + r * NP], sw = sS[2 * nlmax * NP + r * NP];
 			cmac(C[0], av, sv);
 			cmac(C[1], av, sd); cmac(C[1], ad, sv);
 			cmac(C[2], av, sw); cmac(C[2], aw, sv);
@@ -1604,16 +1643,23 @@ extern "C" int sxs_cuda_plan_scan_topk(sxs_cuda_plan *p, int z_lo, int z_hi, int
 				if (dense) {
 					timer_begin(p, 2, st);
 					{
-						const size_t sh = sizeof(double2) * N;
+						const int NPd = sxs_row_pad((int)N);
+						size_t sh = 0; /* set per instantiation: the A stage depends on the pairs per block */
 						const unsigned npair = (unsigned)(N * N);
 #define SXS_DENSE_LAUNCH(LP, J, TPB, MINB)                                                                           \
-	k_cross_dense<LP, J, TPB, MINB><<<dim3((npair + (TPB / LP) - 1) / (TPB / LP), (unsigned)nb, (unsigned)Q), TPB, sh, st>>>( \
-	    L, Q, b1, 0, p->d_At, p->d_St, p->d_tw, p->d_const, p->d_X)
+	do {                                                                                                             \
+		const int ga_ = (int)(((TPB / LP) + N - 1) / N + 1);                                                         \
+		sh = sizeof(double2) * ((size_t)((N + 1) & ~1) + 2 * (size_t)(3 * (L + 1) * NPd + 3 * (L + 1) * ga_));       \
+		if (sh > 48 * 1024) {                                                                                        \
+			cudaFuncSetAttribute(k_cross_dense<LP, J, TPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
+		}                                                                                                            \
+		k_cross_dense<LP, J, TPB, MINB><<<dim3((npair + (TPB / LP) - 1) / (TPB / LP), (unsigned)nb, (unsigned)Q), TPB, sh, st>>>( \
+		    L, Q, b1, 0, p->d_At, p->d_St, p->d_tw, p->d_const, p->d_X);                                              \
+	} while (0)
 						const int variant = getenv("SXS_DENSE_VARIANT") ? atoi(getenv("SXS_DENSE_VARIANT")) : 0; /* tuning */
 						if (L <= 8) SXS_DENSE_LAUNCH(4, 2, 256, 2);
 						else if (L <= 16 && variant == 1) SXS_DENSE_LAUNCH(4, 4, 256, 1);
 						else if (L <= 16 && variant == 2) SXS_DENSE_LAUNCH(8, 2, 256, 2);
-						else if (L <= 16 && variant == 3) SXS_DENSE_LAUNCH(8, 2, 256, 3);
 						else if (L <= 16) SXS_DENSE_LAUNCH(4, 4, 192, 2);
 						else if (L <= 32) SXS_DENSE_LAUNCH(8, 4, 192, 2);
 						else if (L <= 48) SXS_DENSE_LAUNCH(8, 6, 256, 1);

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_scale.py -m gpu -q -rA -p no:cacheprovider -k "ft_rows_to_indices" > gpurun_out/r2v_pytest.txt 2>&1; echo "rc=$?" >> gpurun_out/r2v_pytest.txt
+grep -h "passed\|failed\|rc=\|ft rows ->\|Error\|assert" gpurun_out/r2v_pytest.txt | cut -c1-400 | head
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cross_dense -s 3 -c 1 -o gpurun_out/prof_r2v_dense -f python -m pytest tests/test_gpu_scale.py -m gpu -q -p no:cacheprovider -k "test_dense_scan_topk and not reference" > gpurun_out/r2v_ncu.log 2>&1
+tail -3 gpurun_out/r2v_ncu.log | cut -c1-200
+python scripts/correlate_e2e.py 2000000 2>&1 | tail -8

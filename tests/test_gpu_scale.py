@@ -298,8 +298,8 @@ def test_dense_scan_topk():
     """every grid point of one z step (16 x 16 cells x 31^3 = 7.6 M points) is scored on the device and
     the best 64 come back.  The scan runs the DENSE form of K3 (k_cross_dense: the inner sums of a (g1, g2) pair serve all
     31 values of a2); it must name the points the list form names (SXS_SCAN_LIST=1: the same scan through the list
-    kernels), carry what the list API gives for those indices to rounding, and its K3 must be >= 1.5x faster (measured
-    1.9x: 47 against 91 ms per z; the 3x the round-1 review asked for needs the operands staged in shared memory)."""
+    kernels), carry what the list API gives for those indices to rounding, and its K3 must be >= 1.8x faster (measured
+    2.2x: 41 against 91 ms per z with the operands of every m staged in shared memory; 47 ms with plain loads)."""
     G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
     q, L = G["qvals"], int(G["L"])
     nb, N = L + 1, 2 * L + 1
@@ -324,7 +324,7 @@ def test_dense_scan_topk():
     plan.set_profiling(False)
     print("dense scan of one z: K3 %.1f ms dense form, %.1f ms list form; K4 %.1f / %.1f ms"
           % (t_dense["cross"][0], t_list["cross"][0], t_dense["fit"][0], t_list["fit"][0]))
-    assert t_dense["cross"][0] * 1.5 <= t_list["cross"][0]
+    assert t_dense["cross"][0] * 1.8 <= t_list["cross"][0]
     assert np.array_equal(np.sort(idx), np.sort(idx_l))
     o, ol = np.argsort(idx), np.argsort(idx_l)
     parity.check("dense form vs list form, top-%d" % k, (s[o], c1[o], c2[o]), (s_l[ol], c1_l[ol], c2_l[ol]))
@@ -366,3 +366,54 @@ def test_dense_scan_topk_against_the_reference():
     assert np.isin(ref_in_cell, mine_in_cell).all()                       # nothing better was missed
     assert (rs[np.isin(allpts, mine_in_cell)] <= thr * (1 + 1e-9)).all()    # everything reported belongs
     assert rs.min() >= s[0] * (1 - 1e-9)
+
+
+def test_ft_rows_to_indices_on_the_device_equal_the_host_route():
+    """SURVEY 8f-2 on the device: k_ft_rows_to_index (one thread per ft row: sxs_ft2euler, the three-decimal text round
+    trip as exact arithmetic, z lookup, snapping) gives, row for row, the flat indices of the host route
+    sxs_ft_rows_to_indices64 (itself pinned on the reference's Euler file byte for byte, tests/test_cpu_host.py) —
+    2 M random rows incl. rows off the z table, bad rotation ids, and translations on the axes (degenerate angles)."""
+    import time
+    rng = np.random.default_rng(21)
+    L, nrot, nrows = 15, 70000, 2_000_000
+    qn = rng.normal(size=(nrot, 4))
+    qn /= np.linalg.norm(qn, axis=1)[:, None]
+    w, x, y, z = qn.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w), 2 * (x * y + z * w),
+                  1 - 2 * (x * x + z * z), 2 * (y * z - x * w), 2 * (x * z - y * w), 2 * (y * z + x * w),
+                  1 - 2 * (x * x + y * y)], 1)
+    rot_id = rng.integers(0, nrot, nrows).astype(np.int32)
+    u = rng.normal(size=(nrows, 3))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    ref_lig = np.array([3.0, -2.0, 1.5])
+    dist = rng.uniform(-2.0, 90.0, nrows)
+    trans = u * dist[:, None] - ref_lig
+    # translations whose rounded z lands exactly on table values, and on the coordinate axes
+    trans[:1000] = np.round(trans[:1000] + ref_lig) - ref_lig
+    trans[1000:1003] = np.array([[0, 0, 30.0], [0, 0, -30.0], [30.0, 0, 0]]) - ref_lig
+    zvals = np.arange(1.0, 80.001, 1.0)
+    t0 = time.time()
+    index, ft_id, order = capi.ft_rows_to_indices(rot_id, trans, R, ref_lig, zvals, L)
+    t_host = time.time() - t0
+    want = np.full(nrows, -1, dtype=np.int64)
+    want[order] = index
+    capi.cuda_ft_rows_to_indices(rot_id[:10], trans[:10], R, ref_lig, zvals, L)   # context + module load
+    t0 = time.time()
+    got = capi.cuda_ft_rows_to_indices(rot_id, trans, R, ref_lig, zvals, L)
+    t_dev = time.time() - t0
+    # degenerate rows (0 / 0 angles: translation on the z axis) are dropped by both routes
+    diff = np.flatnonzero(got != want)
+    assert got[1000] == -1 and want[1000] == -1          # (0, 0, +30): b1 = 0, g1 = acos(0 / 0)
+    print("ft rows -> indices, %d rows: host threads %.3f s (%.2f M rows/s), device incl. copies %.3f s (%.2f M rows/s); "
+          "%d kept, %d rows differ" % (nrows, t_host, nrows / t_host / 1e6, t_dev, nrows / t_dev / 1e6, (want >= 0).sum(), len(diff)))
+    assert 0 < (want >= 0).sum() < nrows
+    assert len(diff) == 0, (diff[:10], got[diff[:10]], want[diff[:10]])
+    bad = rot_id[:5].copy()
+    bad[2] = nrot
+    assert capi.cuda_ft_rows_to_indices(bad, trans[:5], R, ref_lig, zvals, L)[2] == -2
+    # L = 30: 64-bit indices
+    i30, _, o30 = capi.ft_rows_to_indices(rot_id[:200000], trans[:200000], R, ref_lig, zvals, 30)
+    w30 = np.full(200000, -1, dtype=np.int64)
+    w30[o30] = i30
+    g30 = capi.cuda_ft_rows_to_indices(rot_id[:200000], trans[:200000], R, ref_lig, zvals, 30)
+    assert np.array_equal(g30, w30) and w30.max() > 2 ** 31
