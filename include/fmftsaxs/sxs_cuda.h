@@ -120,8 +120,9 @@ int sxs_cuda_exp_array(int device, const double *x, long long n, double *y);
  * threads — sxs_ft2euler (src/index.c:38-75), the three-decimal text round trip of the Euler file (src/index.c:114,
  * tools/correlate.c:214), the z table lookup and the snapping of tools/correlate.c:219-247 — one thread per row.
  * rots: nrot row-major 3x3 matrices (struct mol_matrix3 is nine doubles); ref_lig: three host doubles.
- * index[i] = flat 64-bit index of row i, -1 when its z is not on zvals (the tool drops the row), -2 when rot_id[i] is
- * outside the table.  Host arrays; the _dev form takes device arrays and a stream (ref_lig stays a host pointer). */
+ * index[i] = flat 64-bit index of row i, -1 when its z is not on zvals (the tool drops the row) or its geometry is
+ * degenerate (a 0 / 0 angle: the tool's index is built from (int)round(nan) there), -2 when rot_id[i] is outside the
+ * table.  Host arrays; the _dev form takes device arrays and a stream (ref_lig stays a host pointer). */
 int sxs_cuda_ft_rows_to_indices(int device, const int *rot_id, const double *trans, long long n, const double *rots,
                                 long long nrot, const double *ref_lig, const double *zvals, int znum, int L,
                                 long long *index);

@@ -18,7 +18,15 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <limits.h>
+
 #include "index.h"
+
+/* "this row's z is not on the table" — a value of its own, not the sign of the index: a degenerate geometry (beta = 0:
+ * 0 / 0 angles, "nan" in the Euler file) gives the tool's `(int)round(nan)` digits and with them a negative index for a
+ * row that DID match a z; the reference-shaped route keeps such a row (the CUDA layer leaves out-of-range indices
+ * untouched), so this route keeps it too */
+#define SXS_OFF_TABLE LLONG_MIN
 
 struct piece {
 	const char *beg, *end; /* whole lines */
@@ -28,7 +36,7 @@ struct piece {
 	int znum, L, want_text;
 	/* results */
 	long long nrows, cap;
-	long long *flat; /* per row: flat index or -1 */
+	long long *flat; /* per row: flat index, or SXS_OFF_TABLE when the row's z is not on the table */
 	int *rot_id;
 	char *text; size_t text_len, text_cap;
 	int status; /* 0 ok, 1 step aside, 2 rotation index out of range */
@@ -79,10 +87,19 @@ static void *piece_main(void *arg)
 			}
 		}
 		char *endp;
-		char buf[4][48];
-		for (int k = 0; k < 4; k++) {
+		char buf[10][48];
+		for (int k = 0; k < 10; k++) {
 			memcpy(buf[k], tok[k], (size_t)(tend[k] - tok[k]));
 			buf[k][tend[k] - tok[k]] = '\0';
+		}
+		/* the six ignored columns: "%lf" must consume each token whole ("12.3-4.5", "1.5.3", "--" would be split or
+		 * refused by fscanf: such a file goes to the reference-shaped route, which reports it as the reference does) */
+		for (int k = 4; k < 10; k++) {
+			(void)strtod(buf[k], &endp);
+			if (endp == buf[k] || *endp != '\0') {
+				pc->status = 1;
+				return NULL;
+			}
 		}
 		const long id = strtol(buf[0], &endp, 10);
 		if (*endp != '\0') { /* "%d" would stop inside the token */
@@ -117,7 +134,7 @@ static void *piece_main(void *arg)
 			*dst[k] = strtod(q, &endp);
 			q = endp + 1;
 		}
-		long long flat = -1;
+		long long flat = SXS_OFF_TABLE;
 		for (int k = 0; k < pc->znum; k++) {
 			if (pc->zvals[k] > e.z - 0.001 && pc->zvals[k] < e.z + 0.001) {
 				flat = sxs_euler_to_index64(&e, k, pc->L);
@@ -244,7 +261,7 @@ long long sxs_ft_file_to_indices(const char *eu_path, const char *ft_path, const
 		long long row = 0;
 		for (int k = 0; k < nthreads; k++) {
 			for (long long i = 0; i < pcs[k].nrows; i++, row++) {
-				if (pcs[k].flat[i] >= 0) {
+				if (pcs[k].flat[i] != SXS_OFF_TABLE) {
 					(*index)[kept] = pcs[k].flat[i];
 					(*ft_id)[kept] = pcs[k].rot_id[i];
 					(*order)[kept] = (int)row; /* the serial number counts every row */

@@ -8,7 +8,13 @@
 #include <stdlib.h>
 #include <unistd.h>
 
+#include <limits.h>
+
 #include "index.h"
+
+/* see ft_fast.c: off-table is a value of its own, rows with nan-derived (negative) indices are kept like the
+ * reference-shaped route keeps them */
+#define SXS_OFF_TABLE LLONG_MIN
 
 /* what fprintf("% .3f") followed by fscanf("%lf") makes of x (src/index.c:114, tools/correlate.c:214) */
 static double through_text(double x)
@@ -26,7 +32,7 @@ struct rows_job {
 	struct mol_vector3 *ref_lig;
 	const double *zvals;
 	int znum, L;
-	long long *flat; /* per input row: flat index, or -1 when the row is dropped */
+	long long *flat; /* per input row: flat index, or SXS_OFF_TABLE when the row is dropped */
 	int bad;
 };
 
@@ -48,7 +54,7 @@ static void *rows_main(void *arg)
 		e.a2 = through_text(e.a2);
 		e.b2 = through_text(e.b2);
 		e.g2 = through_text(e.g2);
-		long long flat = -1;
+		long long flat = SXS_OFF_TABLE;
 		for (int k = 0; k < j->znum; k++) {
 			if (j->zvals[k] > e.z - 0.001 && j->zvals[k] < e.z + 0.001) {
 				flat = sxs_euler_to_index64(&e, k, j->L);
@@ -111,7 +117,7 @@ long long sxs_ft_rows_to_indices64(long long *index, int *ft_id, int *order, con
 	rows_to_flat(flat, rot_id, trans, n, rots, ref_lig, zvals, znum, L, nthreads);
 	long long kept = 0;
 	for (long long i = 0; i < n; i++) {
-		if (flat[i] >= 0) {
+		if (flat[i] != SXS_OFF_TABLE) {
 			index[kept] = flat[i];
 			ft_id[kept] = rot_id[i];
 			order[kept] = (int)i;
@@ -135,7 +141,7 @@ long long sxs_ft_rows_to_indices(int *index, int *ft_id, int *order, const int *
 	rows_to_flat(flat, rot_id, trans, n, rots, ref_lig, zvals, znum, L, nthreads);
 	long long kept = 0;
 	for (long long i = 0; i < n; i++) {
-		if (flat[i] >= 0) {
+		if (flat[i] != SXS_OFF_TABLE) {
 			index[kept] = (int)flat[i]; /* 32-bit packing like the tool's `int id` (tools/correlate.c:225-240) */
 			ft_id[kept] = rot_id[i];
 			order[kept] = (int)i;

@@ -322,13 +322,27 @@ def test_ft_file_fast_route_equals_the_three_pass_route(capi, tmp_path):
         assert np.array_equal(index, want_index)
     assert fast(ft, None, 2) is not None and all(np.array_equal(a, b) for a, b in zip(fast(ft, None, 2), (index, ft_id, order)))
     # rows the fast parser must not interpret: a token fscanf would split, nan, a short last row
-    for bad in ("3 1.0 2.0 3.0 0 0 0 0 0 0\n4.5 1.0 2.0 3.0 0 0 0 0 0 0\n", "3 nan 2.0 3.0 0 0 0 0 0 0\n", "3 1.0 2.0 3.0 0 0 0 0 0\n"):
+    # ... and, in the six ignored columns, tokens "%lf" would split or refuse (abutting fixed-width fields, two points, signs only)
+    for bad in ("3 1.0 2.0 3.0 0 0 0 0 0 0\n4.5 1.0 2.0 3.0 0 0 0 0 0 0\n", "3 nan 2.0 3.0 0 0 0 0 0 0\n", "3 1.0 2.0 3.0 0 0 0 0 0\n",
+                "3 1.0 2.0 3.0 12.3-4.5 0 0 0 0 0\n", "3 1.0 2.0 3.0 0 1.5.3 0 0 0 0\n", "3 1.0 2.0 3.0 0 0 -- 0 0 0\n"):
         odd = tmp_path / "odd.ft"
         open(odd, "w").write(bad)
         marker = tmp_path / "untouched.txt"
         open(marker, "w").write("keep")
         assert fast(odd, marker, 2) is None
         assert open(marker).read() == "keep"
+    # a degenerate row (ligand centre on the receptor's +z axis: g1 = acos(0 / 0), "nan" in the Euler file) lies on the z
+    # table: the reference-shaped route keeps it with the tool's (int)round(nan) index, and so do the fast routes —
+    # "off the table" is not read off the sign of the index
+    deg = tmp_path / "deg.ft"
+    t_deg = np.array([0.0, 0.0, 30.0]) - ref_lig
+    open(deg, "w").write("%d %.17g %.17g %.17g 0 0 0 0 0 0\n%d %.3f %.3f %.3f 0 0 0 0 0 0\n" % (0, *t_deg, rot_id[0], *trans[keep][0]))
+    i_d, f_d, o_d = fast(deg, tmp_path / "deg_eu.txt", 1)
+    assert "nan" in open(tmp_path / "deg_eu.txt").read().splitlines()[0]
+    assert list(o_d) == [0, 1] and i_d[0] < 0 and i_d[1] == want_index[0]
+    i_m, f_m, o_m = capi.ft_rows_to_indices(np.array([0, rot_id[0]], dtype=np.int32), np.array([t_deg, np.round(trans[keep][0], 3)]), R,
+                                            ref_lig, zvals, L, nthreads=1)
+    assert list(o_m) == [0, 1] and i_m[0] == i_d[0]
     # rows may be spread over lines differently: fscanf does not care, neither does the fast route
     text = open(ft).read().split("\n")
     open(tmp_path / "wrapped.ft", "w").write("\n".join(l.replace(" 0.0 0 ", " 0.0\n0 ", 1) for l in text))
