@@ -93,6 +93,10 @@ int sxs_cuda_plan_fit_evaluations(sxs_cuda_plan *plan, long long *hist64);
 int sxs_cuda_plan_set_profiling(sxs_cuda_plan *plan, int on);
 int sxs_cuda_plan_kernel_times(sxs_cuda_plan *plan, double *ms5, long long *launches5);
 
+/* Pinned host memory owned by the plan (grow-only, freed with it); NULL on failure.  The host layer stages the compact
+ * index list and the result columns of a z shard in it. */
+void *sxs_cuda_plan_host_buffer(sxs_cuda_plan *plan, size_t bytes);
+
 /* Dense scan (the reference's skip = 0 mode of src/fftsaxs.c:867-872 computes every point of every cell
  * but reports only listed rows): every grid point (b1, b2, a2, g1, g2) of the z steps [z_lo, z_hi) is scored and the
  * k points of lowest chi are returned, chi ascending: flat 64-bit index (-1 = empty slot), chi, c1, c2.  Host arrays

@@ -98,6 +98,7 @@ struct sxs_cuda_plan {
 	double *d_out3; size_t cap_out3;
 	long long *h_zoff;
 	void *h_pinned; size_t cap_pinned;
+	void *h_shard; size_t cap_shard; /* pinned staging of a z shard's compact list and results (sxs_cuda_plan_host_buffer) */
 	/* budgets */
 	size_t budget_St, budget_X;
 	long long stats[5];
@@ -239,6 +240,9 @@ extern "C" void sxs_cuda_plan_destroy(sxs_cuda_plan *p)
 	}
 	if (p->h_zoff != NULL) {
 		cudaFreeHost(p->h_zoff);
+	}
+	if (p->h_shard != NULL) {
+		cudaFreeHost(p->h_shard);
 	}
 	if (p->h_pinned != NULL) {
 		cudaFreeHost(p->h_pinned);
@@ -1769,6 +1773,27 @@ static int score_host(sxs_cuda_plan *p, const IndexT *index, long long nout, int
 		c2[r] = h3[2 * (size_t)nout + r];
 	}
 	return 0;
+}
+
+/* pinned host memory owned by the plan (grow-only, freed with it): the host layer stages a shard's compact index list
+ * and its three result columns here, so that the copies of sxs_cuda_plan_score_* run at the pinned rate */
+extern "C" void *sxs_cuda_plan_host_buffer(sxs_cuda_plan *p, size_t bytes)
+{
+	if (cudaSetDevice(p->device) != cudaSuccess) {
+		return NULL;
+	}
+	if (bytes > p->cap_shard) {
+		if (p->h_shard) cudaFreeHost(p->h_shard);
+		p->h_shard = NULL;
+		p->cap_shard = 0;
+		if (cudaHostAlloc(&p->h_shard, bytes + bytes / 8, cudaHostAllocPortable) != cudaSuccess) {
+			sxs_cuda_set_error("cudaHostAlloc of %zu bytes failed", bytes);
+			p->h_shard = NULL;
+			return NULL;
+		}
+		p->cap_shard = bytes + bytes / 8;
+	}
+	return p->h_shard;
 }
 
 extern "C" int sxs_cuda_plan_score_i32(sxs_cuda_plan *p, const int *index, long long nout, int z_lo, int z_hi,

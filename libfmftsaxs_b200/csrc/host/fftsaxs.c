@@ -11,6 +11,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <unistd.h>
 
 #include "fftsaxs.h"
 #include "sxs_host.h"
@@ -100,63 +101,131 @@ struct shard_job {
 	const long long *idx64;
 	long long nout;
 	double *scores, *c1, *c2;
-	long long cell5; /* grid points per z step: index / cell5 = z digit */
-	int compact;     /* several devices: this shard extracts its own rows first (see shard_main) */
-	long long rows;  /* rows this shard scored */
+	/* several devices: the rows of this shard's z range, extracted by partition_rows() */
+	int compact;
+	long long rows;      /* rows of the shard */
+	long long *pos;      /* their positions in the caller's list */
+	void *sub;           /* their indices (int or long long), in the plan's pinned buffer */
+	double *out;         /* [3][rows] results, same buffer */
 	int rc;
 	char err[512]; /* the CUDA layer's message of this thread (its error buffer is thread-local) */
 };
 
-/* With several devices every shard first extracts the rows of its own z range — one pass over the index list on
- * its own host thread — and hands the device that compact list only: uploads, the key sort and the scatter then
- * scale with the shard, not with the whole list (the reference's MPI ranks do the same filtering while reading the
- * Euler file, tools/correlate.c:169-251).  Results go back to the caller's arrays at the rows' input positions;
- * rows outside every range are never written. */
+/* ---- rows -> z shards on host threads ---------------------------------------------------------------------------
+ * With several devices every device gets the rows of its own z range as a compact list, so that uploads, the key sort
+ * and the scatter scale with the shard and not with the whole list (the reference's MPI ranks do the same filtering
+ * while reading the Euler file, tools/correlate.c:169-251).  Two passes over the list, both split over host threads:
+ * (1) z digit of every row (kept, two bytes per row) and a histogram per thread — the shard boundaries follow from the
+ * summed histogram; (2) every thread writes its rows into the shards' lists at offsets known from the histograms, so
+ * the lists keep the input order.  The z digit is index / cell5; it is taken through a reciprocal and corrected with
+ * two multiplications instead of a 64-bit division per row (the r2x 8-GPU run spent more time in those divisions —
+ * three passes, two of them once per device — than on the GPUs). */
+#define SXS_Z_NONE 0xFFFFu
+struct part_job {
+	const int *idx32;
+	const long long *idx64;
+	long long i0, i1, cell5;
+	int znum, nshard;
+	unsigned short *zdig;
+	long long *cnt;            /* [znum] rows per z digit in [i0, i1) */
+	const int *shard_of_z;     /* pass 2 */
+	long long *off;            /* [nshard] write offsets of this thread, pass 2 */
+	struct shard_job *jobs;
+};
+
+static void *part_pass1(void *arg)
+{
+	struct part_job *j = (struct part_job *)arg;
+	const double inv = 1.0 / (double)j->cell5;
+	for (long long i = j->i0; i < j->i1; i++) {
+		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
+		unsigned short zd = SXS_Z_NONE;
+		if (v >= 0) {
+			long long z = (long long)((double)v * inv);
+			if (z * j->cell5 > v) {
+				z--;
+			} else if ((z + 1) * j->cell5 <= v) {
+				z++;
+			}
+			if (z < j->znum) {
+				zd = (unsigned short)z;
+				j->cnt[z]++;
+			}
+		}
+		j->zdig[i] = zd;
+	}
+	return NULL;
+}
+
+static void *part_pass2(void *arg)
+{
+	struct part_job *j = (struct part_job *)arg;
+	for (long long i = j->i0; i < j->i1; i++) {
+		const unsigned short zd = j->zdig[i];
+		if (zd == SXS_Z_NONE) {
+			continue;
+		}
+		const int s = j->shard_of_z[zd];
+		if (s < 0) {
+			continue;
+		}
+		struct shard_job *sj = &j->jobs[s];
+		const long long k = j->off[s]++;
+		sj->pos[k] = i;
+		if (j->idx32 != NULL) {
+			((int *)sj->sub)[k] = j->idx32[i];
+		} else {
+			((long long *)sj->sub)[k] = j->idx64[i];
+		}
+	}
+	return NULL;
+}
+
+static int host_threads(long long n)
+{
+	int t = getenv("SXS_HOST_THREADS") ? atoi(getenv("SXS_HOST_THREADS")) : (int)sysconf(_SC_NPROCESSORS_ONLN);
+	if (t > 32) t = 32;
+	if ((long long)t > n / 65536 + 1) t = (int)(n / 65536 + 1);
+	return t < 1 ? 1 : t;
+}
+
+static void run_threads(void *(*fn)(void *), struct part_job *pj, int nt)
+{
+	pthread_t th[32];
+	int started = 0;
+	for (int k = 1; k < nt; k++) {
+		if (pthread_create(&th[k], NULL, fn, &pj[k]) != 0) {
+			break;
+		}
+		started = k;
+	}
+	fn(&pj[0]);
+	for (int k = started + 1; k < nt; k++) {
+		fn(&pj[k]);
+	}
+	for (int k = 1; k <= started; k++) {
+		pthread_join(th[k], NULL);
+	}
+}
+
 static int shard_score_compact(struct shard_job *j)
 {
-	long long n = 0;
-	for (long long i = 0; i < j->nout; i++) {
-		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
-		n += v >= 0 && v / j->cell5 >= j->z_lo && v / j->cell5 < j->z_hi;
-	}
-	j->rows = n;
+	const long long n = j->rows;
 	if (n == 0) {
 		return 0;
 	}
-	long long *pos = (long long *)malloc(sizeof(long long) * (size_t)n);
-	void *sub = malloc((j->idx32 != NULL ? sizeof(int) : sizeof(long long)) * (size_t)n);
-	double *out = (double *)malloc(sizeof(double) * 3 * (size_t)n);
-	if (pos == NULL || sub == NULL || out == NULL) {
-		free(pos); free(sub); free(out);
-		snprintf(j->err, sizeof(j->err), "out of host memory for a shard of %lld rows", n);
-		return -1;
-	}
-	long long k = 0;
-	for (long long i = 0; i < j->nout; i++) {
-		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
-		if (v >= 0 && v / j->cell5 >= j->z_lo && v / j->cell5 < j->z_hi) {
-			pos[k] = i;
-			if (j->idx32 != NULL) {
-				((int *)sub)[k] = j->idx32[i];
-			} else {
-				((long long *)sub)[k] = v;
-			}
-			out[k] = j->scores[i]; out[n + k] = j->c1[i]; out[2 * n + k] = j->c2[i];
-			k++;
-		}
-	}
 	int rc;
 	if (j->idx32 != NULL) {
-		rc = sxs_cuda_plan_score_i32(j->plan, (const int *)sub, n, j->z_lo, j->z_hi, out, out + n, out + 2 * n);
+		rc = sxs_cuda_plan_score_i32(j->plan, (const int *)j->sub, n, j->z_lo, j->z_hi, j->out, j->out + n, j->out + 2 * n);
 	} else {
-		rc = sxs_cuda_plan_score_i64(j->plan, (const long long *)sub, n, j->z_lo, j->z_hi, out, out + n, out + 2 * n);
+		rc = sxs_cuda_plan_score_i64(j->plan, (const long long *)j->sub, n, j->z_lo, j->z_hi, j->out, j->out + n, j->out + 2 * n);
 	}
 	if (rc == 0) {
-		for (k = 0; k < n; k++) {
-			j->scores[pos[k]] = out[k]; j->c1[pos[k]] = out[n + k]; j->c2[pos[k]] = out[2 * n + k];
+		/* every row of the compact list lies in [z_lo, z_hi): all of them were scored */
+		for (long long k = 0; k < n; k++) {
+			j->scores[j->pos[k]] = j->out[k]; j->c1[j->pos[k]] = j->out[n + k]; j->c2[j->pos[k]] = j->out[2 * n + k];
 		}
 	}
-	free(pos); free(sub); free(out);
 	return rc;
 }
 
@@ -202,11 +271,25 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	const size_t ncoef = (size_t)3 * qnum * nb * nb * 2;
 	double *coefA = (double *)malloc(sizeof(double) * ncoef);
 	double *coefB = (double *)malloc(sizeof(double) * ncoef);
-	double *bessel = (double *)malloc(sizeof(double) * (size_t)znum * qnum * N);
-	CHECK_PTR(coefA); CHECK_PTR(coefB); CHECK_PTR(bessel);
+	CHECK_PTR(coefA); CHECK_PTR(coefB);
 	sxs_spf_full_pack(A, coefA);
 	sxs_spf_full_pack(B, coefB);
-	sxs_fill_bessel_table(bessel, zvals, znum, qvals, qnum, L);
+	/* j_p(q z) with the reference-exact series: znum*qnum*(2L+1) values, ~10 ms for the 64 x 50 x 31 table of config 3 —
+	 * kept between calls with the same (z table, q grid, L) (callers score list after list on one table) */
+	static struct { double *tab, *z, *q; int znum, qnum, L; } bc;
+	if (bc.tab == NULL || bc.znum != znum || bc.qnum != qnum || bc.L != L || memcmp(bc.z, zvals, sizeof(double) * znum) ||
+	    memcmp(bc.q, qvals, sizeof(double) * qnum)) {
+		free(bc.tab); free(bc.z); free(bc.q);
+		bc.tab = (double *)malloc(sizeof(double) * (size_t)znum * qnum * N);
+		bc.z = (double *)malloc(sizeof(double) * znum);
+		bc.q = (double *)malloc(sizeof(double) * qnum);
+		CHECK_PTR(bc.tab); CHECK_PTR(bc.z); CHECK_PTR(bc.q);
+		memcpy(bc.z, zvals, sizeof(double) * znum);
+		memcpy(bc.q, qvals, sizeof(double) * qnum);
+		bc.znum = znum; bc.qnum = qnum; bc.L = L;
+		sxs_fill_bessel_table(bc.tab, zvals, znum, qvals, qnum, L);
+	}
+	const double *bessel = bc.tab;
 
 	/* rows per z digit -> contiguous z ranges of roughly equal row count, one per device */
 	int dev[SXS_MAX_DEV];
@@ -215,15 +298,30 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	CHECK_PTR(per_z);
 	const long long cell5 = (long long)nb * nb * N * N * N;
 	long long total = 0;
-	if (ndev == 1) {
+	unsigned short *zdig = NULL;
+	struct part_job pj[32];
+	long long *cnt_all = NULL;
+	int nt = 1;
+	if (ndev == 1 || znum >= (int)SXS_Z_NONE) {
 		/* one device takes the whole z table: no need to look at the list on the host */
+		ndev = 1;
 		per_z[0] = total = nout;
 	} else {
-		for (long long i = 0; i < nout; i++) {
-			long long v = idx32 != NULL ? (long long)idx32[i] : idx64[i];
-			if (v >= 0 && v / cell5 < znum) {
-				per_z[v / cell5]++;
-				total++;
+		nt = host_threads(nout);
+		zdig = (unsigned short *)malloc(sizeof(unsigned short) * (size_t)nout);
+		cnt_all = (long long *)calloc((size_t)nt * znum, sizeof(long long));
+		CHECK_PTR(zdig); CHECK_PTR(cnt_all);
+		for (int k = 0; k < nt; k++) {
+			memset(&pj[k], 0, sizeof(pj[k]));
+			pj[k].idx32 = idx32; pj[k].idx64 = idx64; pj[k].cell5 = cell5; pj[k].znum = znum; pj[k].zdig = zdig;
+			pj[k].i0 = nout * k / nt; pj[k].i1 = nout * (k + 1) / nt;
+			pj[k].cnt = cnt_all + (size_t)k * znum;
+		}
+		run_threads(part_pass1, pj, nt);
+		for (int k = 0; k < nt; k++) {
+			for (int z = 0; z < znum; z++) {
+				per_z[z] += pj[k].cnt[z];
+				total += pj[k].cnt[z];
 			}
 		}
 	}
@@ -234,18 +332,25 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	if (ndev > nz_used) {
 		ndev = nz_used > 0 ? nz_used : 1;
 	}
-	if (ndev == 1) {
+	const int whole = ndev == 1;
+	if (whole) {
 		per_z[0] = 0; /* the single shard below spans [0, znum) regardless of the histogram */
 	}
 
 	struct shard_job jobs[SXS_MAX_DEV];
 	pthread_t threads[SXS_MAX_DEV];
+	int *shard_of_z = (int *)malloc(sizeof(int) * (size_t)znum);
+	CHECK_PTR(shard_of_z);
+	for (int z = 0; z < znum; z++) {
+		shard_of_z[z] = -1;
+	}
 	int z_next = 0;
 	long long done = 0;
 	int njobs = 0;
 	for (int d = 0; d < ndev; d++) {
 		long long want = (total * (d + 1)) / ndev;
 		int z_lo = z_next;
+		const long long done_before = done;
 		while (z_next < znum && (done < want || d == ndev - 1)) {
 			done += per_z[z_next++];
 			if (d < ndev - 1 && done >= want) {
@@ -258,7 +363,7 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 		if (z_next == z_lo) {
 			continue;
 		}
-		struct shard_job *j = &jobs[njobs++];
+		struct shard_job *j = &jobs[njobs];
 		memset(j, 0, sizeof(*j));
 		j->plan = plan_for(dev[d], L, qnum, qvals, t);
 		j->coefA = coefA; j->coefB = coefB; j->a = params->a; j->bessel = bessel;
@@ -266,11 +371,48 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 		j->znum = znum; j->z_lo = z_lo; j->z_hi = z_next;
 		j->idx32 = idx32; j->idx64 = idx64; j->nout = nout;
 		j->scores = scores; j->c1 = c1; j->c2 = c2;
-		j->cell5 = cell5;
+		j->rows = done - done_before;
+		for (int z = z_lo; z < z_next; z++) {
+			shard_of_z[z] = njobs;
+		}
+		njobs++;
 	}
-	for (int k = 0; k < njobs; k++) {
-		jobs[k].compact = njobs > 1;
+	if (!whole && njobs > 0) {
+		/* the shards' lists: positions on the heap, indices and results in each plan's pinned buffer */
+		const size_t isz = idx32 != NULL ? sizeof(int) : sizeof(long long);
+		for (int k = 0; k < njobs; k++) {
+			struct shard_job *j = &jobs[k];
+			j->compact = 1;
+			const size_t n = (size_t)(j->rows > 0 ? j->rows : 1);
+			const size_t sub_bytes = (isz * n + 15) & ~(size_t)15;
+			j->pos = (long long *)malloc(sizeof(long long) * n);
+			unsigned char *buf = (unsigned char *)sxs_cuda_plan_host_buffer(j->plan, sub_bytes + sizeof(double) * 3 * n);
+			if (j->pos == NULL || buf == NULL) {
+				ERROR_MSG("out of host memory for the z shards of the pose list");
+			}
+			j->sub = buf;
+			j->out = (double *)(buf + sub_bytes);
+		}
+		long long *off_all = (long long *)calloc((size_t)nt * njobs, sizeof(long long));
+		CHECK_PTR(off_all);
+		for (int s = 0; s < njobs; s++) {
+			long long run = 0;
+			for (int k = 0; k < nt; k++) {
+				off_all[(size_t)k * njobs + s] = run;
+				for (int z = jobs[s].z_lo; z < jobs[s].z_hi; z++) {
+					run += pj[k].cnt[z];
+				}
+			}
+		}
+		for (int k = 0; k < nt; k++) {
+			pj[k].shard_of_z = shard_of_z; pj[k].off = off_all + (size_t)k * njobs; pj[k].jobs = jobs; pj[k].nshard = njobs;
+		}
+		run_threads(part_pass2, pj, nt);
+		free(off_all);
 	}
+	free(zdig);
+	free(cnt_all);
+	free(shard_of_z);
 	if (njobs == 1) {
 		shard_main(&jobs[0]);
 	} else {
@@ -284,13 +426,15 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 		}
 	}
 	for (int k = 0; k < njobs; k++) {
+		free(jobs[k].pos);
+	}
+	for (int k = 0; k < njobs; k++) {
 		if (jobs[k].rc != 0) {
 			fprintf(stderr, "[Error] sxs_compute_saxs_scores: CUDA layer failed: %s\n", jobs[k].err);
 			exit(EXIT_FAILURE);
 		}
 	}
 	free(per_z);
-	free(bessel);
 	free(coefA);
 	free(coefB);
 	pthread_mutex_unlock(&g_score_lock);
