@@ -1352,8 +1352,13 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 	const int N = 2 * L + 1, ML = sxs_ml_count(L), NP = sxs_row_pad(N), H = (N - 1) / 2;
 	const int GA = (TPB / LP + N - 1) / N + 1; /* g1 values the block's TPB / LP consecutive pairs can span */
 	const int nlmax = L + 1;
+	/* rows of the S stage NP + 2 (LP = 4) or NP + 1 (LP = 8) elements apart, so that the rows a quarter warp reads (the
+	 * LP lanes of a pair read the same g2 of LP consecutive rows) fall on disjoint banks; measured: no effect on the
+	 * kernel's time (41.2 -> 42.9 ms per z, r2z), the 105 M bank conflicts per launch of the unpadded form are not what
+	 * bounds it */
+	const int NPS = NP + (LP == 4 ? 2 : 1);
 	double2 *s_tw = s_dense;
-	const int stage_elems = 3 * nlmax * NP + 3 * nlmax * GA;
+	const int stage_elems = 3 * nlmax * NPS + 3 * nlmax * GA;
 	double2 *stage0 = s_dense + ((N + 1) & ~1);
 	for (int i = threadIdx.x; i < N; i += blockDim.x) {
 		s_tw[i] = tw[i];
@@ -1377,7 +1382,8 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 		const int s_cnt = nl * NP;
 		for (int i = threadIdx.x; i < 3 * s_cnt; i += TPB) {
 			const int c = i / s_cnt, r = i - c * s_cnt;
-			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + c * nlmax * NP + r);
+			const int rl = r / NP, col = r - rl * NP;
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + c * nlmax * NPS + rl * NPS + col);
 			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_base + c * cstride + (size_t)row0 * NP + r) : "memory");
 		}
 		const int a_cnt = nl * GA;
@@ -1385,7 +1391,7 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 			const int c = i / a_cnt, r = i - c * a_cnt;
 			const int rl = r / GA, gi = r - rl * GA;
 			const int gg = min(g1base + gi, NP - 1);
-			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + 3 * nlmax * NP + c * nlmax * GA + r);
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + 3 * nlmax * NPS + c * nlmax * GA + r);
 			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a_base + c * cstride + (size_t)(row0 + rl) * NP + gg) : "memory");
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1414,7 +1420,7 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 		if (m < L) {
 			stage_fill(stage0 + ((m + 1) & 1) * stage_elems, m + 1, row0 + L + 1 - m);
 		}
-		const double2 *sS = stg + g2, *sA = stg + 3 * nlmax * NP + ga;
+		const double2 *sS = stg + g2, *sA = stg + 3 * nlmax * NPS + ga;
 		double2 C[6];
 #pragma unroll
 		for (int c = 0; c < 6; c++) {
@@ -1422,7 +1428,7 @@ k_cross_dense(int L, int qnum, int b1, int slab0, const double2 *__restrict__ At
 		}
 		for (int r = lane4; r <= L - m; r += LP) {
 			const double2 av = sA[r * GA], ad = sA[nlmax * GA + r * GA], aw = sA[2 * nlmax * GA + r * GA];
-			const double2 sv = sS[r * NP], sd = sS[nlmax * NP + r * NP], sw = sS[2 * nlmax * NP + r * NP];
+			const double2 sv = sS[r * NPS], sd = sS[nlmax * NPS + r * NPS], sw = sS[2 * nlmax * NPS + r * NPS];
 			cmac(C[0], av, sv);
 			cmac(C[1], av, sd); cmac(C[1], ad, sv);
 			cmac(C[2], av, sw); cmac(C[2], aw, sv);
@@ -1653,7 +1659,7 @@ extern "C" int sxs_cuda_plan_scan_topk(sxs_cuda_plan *p, int z_lo, int z_hi, int
 #define SXS_DENSE_LAUNCH(LP, J, TPB, MINB)                                                                           \
 	do {                                                                                                             \
 		const int ga_ = (int)(((TPB / LP) + N - 1) / N + 1);                                                         \
-		sh = sizeof(double2) * ((size_t)((N + 1) & ~1) + 2 * (size_t)(3 * (L + 1) * NPd + 3 * (L + 1) * ga_));       \
+		sh = sizeof(double2) * ((size_t)((N + 1) & ~1) + 2 * (size_t)(3 * (L + 1) * (NPd + 2) + 3 * (L + 1) * ga_)); \
 		if (sh > 48 * 1024) {                                                                                        \
 			cudaFuncSetAttribute(k_cross_dense<LP, J, TPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); \
 		}                                                                                                            \
