@@ -1488,7 +1488,21 @@ LQ_FN int lq_step_a(struct lq_state *s)
 
 /* Part B — the iteration boundary (lbfgsb.c mainlb, labels 222..777): convergence tests, BFGS update, generalised
  * Cauchy point, subspace minimisation, line-search set-up and its first turn.  Returns LQ_NEED_EVAL or LQ_DONE. */
+LQ_FN int lq_step_b_body(struct lq_state *s, const double pgtol, const double tol);
 LQ_FN int lq_step_b(struct lq_state *s, const double pgtol, const double tol)
+{
+	const int r = lq_step_b_body(s, pgtol, tol);
+	LQ_UNROLL
+	for (int i = 1; i <= LQ_M; i++) {
+		LQ_UNROLL
+		for (int j = 1; j <= LQ_M; j++) {
+			s->wt[i][j] = 0.0; /* dead until the next boundary forms it again */
+		}
+	}
+	return r;
+}
+
+LQ_FN int lq_step_b_body(struct lq_state *s, const double pgtol, const double tol)
 {
 	/* entry: 0 = test convergence of a first evaluation, 1 = accepted iterate, 2 = new iteration */
 	int entry = s->phase == LQ_PH_B_NEW_ITER ? 2 : s->phase == LQ_PH_B_ACCEPTED ? 1 : s->phase == LQ_PH_B_FIRST ? 0 : -1;
@@ -1544,9 +1558,13 @@ LQ_FN int lq_step_b(struct lq_state *s, const double pgtol, const double tol)
 				s->updatd = 1;
 				++s->iupdat;
 				lq_matupd(s, rr, dr);
-				if (lq_formt(s) != 0) {
-					lq_reset_memory(s);
-				}
+			}
+			/* The vendored code forms T only after an update and keeps its factor otherwise.  Here it is formed at every
+			 * boundary that has corrections: without an update theta, S'S, S'Y and col are unchanged, so the same
+			 * factor comes out — and wt need not survive from one iteration to the next (lq_step_b clears it on the
+			 * way out: 9 doubles less to keep per fit across the objective). */
+			if (s->col > 0 && lq_formt(s) != 0) {
+				lq_reset_memory(s);
 			}
 			entry = 2;
 		}
