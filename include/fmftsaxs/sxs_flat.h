@@ -54,6 +54,14 @@ void sxs_flat_tables(int L, double *dsymb, double *dwig, double *twiddle);
 /* j_p(q z) table as the scoring call builds it */
 void sxs_flat_bessel_table(const double *zvals, int znum, const double *qvals, int qnum, int L, double *bessel);
 
+/* Test access to the host partition of a pose list over z shards (csrc/host/partition.c; what
+ * sxs_compute_saxs_scores does with several devices).  Exactly one of idx32 / idx64 is non-NULL; cell5 = grid points per
+ * z step.  Fills z_lo/z_hi/rows per shard and, shard after shard, the positions and indices of the shards' rows
+ * (pos_concat, sub_concat: nout entries each).  Returns the number of shards, negated when the list was left whole. */
+int sxs_flat_partition_rows(const int *idx32, const long long *idx64, long long nout, long long cell5, int znum,
+                            int nshard_max, int *z_lo, int *z_hi, long long *rows, long long *pos_concat,
+                            long long *sub_concat);
+
 #ifdef __cplusplus
 }
 #endif

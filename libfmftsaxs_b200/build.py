@@ -17,7 +17,7 @@ OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libfmftsaxs.so")
 
 HOST_SRC = ["sfbessel.c", "saxs_utils.c", "tables.c", "form_factor_table.c", "pdb2spf.c", "profile.c",
-            "min_saxs.c", "index.c", "index_rows.c", "ft_fast.c", "fftsaxs.c", "mol2_mini.c", "flat_api.c"]
+            "min_saxs.c", "index.c", "index_rows.c", "ft_fast.c", "fftsaxs.c", "partition.c", "mol2_mini.c", "flat_api.c"]
 CUDA_SRC = [("sxs_score.cu", []), ("sxs_expand.cu", []), ("sxs_exact.cu", ["-fmad=false"])]
 TOOLS = ["correlate", "single_saxs", "score_ft_naive"]
 

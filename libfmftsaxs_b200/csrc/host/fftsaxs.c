@@ -111,103 +111,6 @@ struct shard_job {
 	char err[512]; /* the CUDA layer's message of this thread (its error buffer is thread-local) */
 };
 
-/* ---- rows -> z shards on host threads ---------------------------------------------------------------------------
- * With several devices every device gets the rows of its own z range as a compact list, so that uploads, the key sort
- * and the scatter scale with the shard and not with the whole list (the reference's MPI ranks do the same filtering
- * while reading the Euler file, tools/correlate.c:169-251).  Two passes over the list, both split over host threads:
- * (1) z digit of every row (kept, two bytes per row) and a histogram per thread — the shard boundaries follow from the
- * summed histogram; (2) every thread writes its rows into the shards' lists at offsets known from the histograms, so
- * the lists keep the input order.  The z digit is index / cell5; it is taken through a reciprocal and corrected with
- * two multiplications instead of a 64-bit division per row (the r2x 8-GPU run spent more time in those divisions —
- * three passes, two of them once per device — than on the GPUs). */
-#define SXS_Z_NONE 0xFFFFu
-struct part_job {
-	const int *idx32;
-	const long long *idx64;
-	long long i0, i1, cell5;
-	int znum, nshard;
-	unsigned short *zdig;
-	long long *cnt;            /* [znum] rows per z digit in [i0, i1) */
-	const int *shard_of_z;     /* pass 2 */
-	long long *off;            /* [nshard] write offsets of this thread, pass 2 */
-	struct shard_job *jobs;
-};
-
-static void *part_pass1(void *arg)
-{
-	struct part_job *j = (struct part_job *)arg;
-	const double inv = 1.0 / (double)j->cell5;
-	for (long long i = j->i0; i < j->i1; i++) {
-		const long long v = j->idx32 != NULL ? (long long)j->idx32[i] : j->idx64[i];
-		unsigned short zd = SXS_Z_NONE;
-		if (v >= 0) {
-			long long z = (long long)((double)v * inv);
-			if (z * j->cell5 > v) {
-				z--;
-			} else if ((z + 1) * j->cell5 <= v) {
-				z++;
-			}
-			if (z < j->znum) {
-				zd = (unsigned short)z;
-				j->cnt[z]++;
-			}
-		}
-		j->zdig[i] = zd;
-	}
-	return NULL;
-}
-
-static void *part_pass2(void *arg)
-{
-	struct part_job *j = (struct part_job *)arg;
-	for (long long i = j->i0; i < j->i1; i++) {
-		const unsigned short zd = j->zdig[i];
-		if (zd == SXS_Z_NONE) {
-			continue;
-		}
-		const int s = j->shard_of_z[zd];
-		if (s < 0) {
-			continue;
-		}
-		struct shard_job *sj = &j->jobs[s];
-		const long long k = j->off[s]++;
-		sj->pos[k] = i;
-		if (j->idx32 != NULL) {
-			((int *)sj->sub)[k] = j->idx32[i];
-		} else {
-			((long long *)sj->sub)[k] = j->idx64[i];
-		}
-	}
-	return NULL;
-}
-
-static int host_threads(long long n)
-{
-	int t = getenv("SXS_HOST_THREADS") ? atoi(getenv("SXS_HOST_THREADS")) : (int)sysconf(_SC_NPROCESSORS_ONLN);
-	if (t > 32) t = 32;
-	if ((long long)t > n / 65536 + 1) t = (int)(n / 65536 + 1);
-	return t < 1 ? 1 : t;
-}
-
-static void run_threads(void *(*fn)(void *), struct part_job *pj, int nt)
-{
-	pthread_t th[32];
-	int started = 0;
-	for (int k = 1; k < nt; k++) {
-		if (pthread_create(&th[k], NULL, fn, &pj[k]) != 0) {
-			break;
-		}
-		started = k;
-	}
-	fn(&pj[0]);
-	for (int k = started + 1; k < nt; k++) {
-		fn(&pj[k]);
-	}
-	for (int k = 1; k <= started; k++) {
-		pthread_join(th[k], NULL);
-	}
-}
-
 static int shard_score_compact(struct shard_job *j)
 {
 	const long long n = j->rows;
@@ -291,95 +194,32 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 	}
 	const double *bessel = bc.tab;
 
-	/* rows per z digit -> contiguous z ranges of roughly equal row count, one per device */
+	/* rows per z digit -> contiguous z ranges of roughly equal row count, one per device (partition.c) */
 	int dev[SXS_MAX_DEV];
-	int ndev = sxs_host_device_list(dev, SXS_MAX_DEV);
-	long long *per_z = (long long *)calloc((size_t)znum, sizeof(long long));
-	CHECK_PTR(per_z);
+	const int ndev = sxs_host_device_list(dev, SXS_MAX_DEV);
 	const long long cell5 = (long long)nb * nb * N * N * N;
-	long long total = 0;
-	unsigned short *zdig = NULL;
-	struct part_job pj[32];
-	long long *cnt_all = NULL;
-	int nt = 1;
-	if (ndev == 1 || znum >= (int)SXS_Z_NONE) {
-		/* one device takes the whole z table: no need to look at the list on the host */
-		ndev = 1;
-		per_z[0] = total = nout;
-	} else {
-		nt = host_threads(nout);
-		zdig = (unsigned short *)malloc(sizeof(unsigned short) * (size_t)nout);
-		cnt_all = (long long *)calloc((size_t)nt * znum, sizeof(long long));
-		CHECK_PTR(zdig); CHECK_PTR(cnt_all);
-		for (int k = 0; k < nt; k++) {
-			memset(&pj[k], 0, sizeof(pj[k]));
-			pj[k].idx32 = idx32; pj[k].idx64 = idx64; pj[k].cell5 = cell5; pj[k].znum = znum; pj[k].zdig = zdig;
-			pj[k].i0 = nout * k / nt; pj[k].i1 = nout * (k + 1) / nt;
-			pj[k].cnt = cnt_all + (size_t)k * znum;
-		}
-		run_threads(part_pass1, pj, nt);
-		for (int k = 0; k < nt; k++) {
-			for (int z = 0; z < znum; z++) {
-				per_z[z] += pj[k].cnt[z];
-				total += pj[k].cnt[z];
-			}
-		}
-	}
-	int nz_used = 0;
-	for (int z = 0; z < znum; z++) {
-		nz_used += per_z[z] > 0;
-	}
-	if (ndev > nz_used) {
-		ndev = nz_used > 0 ? nz_used : 1;
-	}
-	const int whole = ndev == 1;
-	if (whole) {
-		per_z[0] = 0; /* the single shard below spans [0, znum) regardless of the histogram */
-	}
+	struct sxs_partition part;
+	sxs_partition_plan(&part, idx32, idx64, nout, cell5, znum, ndev < SXS_PART_MAX ? ndev : SXS_PART_MAX);
 
 	struct shard_job jobs[SXS_MAX_DEV];
 	pthread_t threads[SXS_MAX_DEV];
-	int *shard_of_z = (int *)malloc(sizeof(int) * (size_t)znum);
-	CHECK_PTR(shard_of_z);
-	for (int z = 0; z < znum; z++) {
-		shard_of_z[z] = -1;
-	}
-	int z_next = 0;
-	long long done = 0;
-	int njobs = 0;
-	for (int d = 0; d < ndev; d++) {
-		long long want = (total * (d + 1)) / ndev;
-		int z_lo = z_next;
-		const long long done_before = done;
-		while (z_next < znum && (done < want || d == ndev - 1)) {
-			done += per_z[z_next++];
-			if (d < ndev - 1 && done >= want) {
-				break;
-			}
-		}
-		if (d == ndev - 1) {
-			z_next = znum;
-		}
-		if (z_next == z_lo) {
-			continue;
-		}
-		struct shard_job *j = &jobs[njobs];
+	const int njobs = part.nshard;
+	for (int k = 0; k < njobs; k++) {
+		struct shard_job *j = &jobs[k];
 		memset(j, 0, sizeof(*j));
-		j->plan = plan_for(dev[d], L, qnum, qvals, t);
+		j->plan = plan_for(dev[k], L, qnum, qvals, t);
 		j->coefA = coefA; j->coefB = coefB; j->a = params->a; j->bessel = bessel;
 		j->mult = params->mult; j->peak = params->peak;
-		j->znum = znum; j->z_lo = z_lo; j->z_hi = z_next;
+		j->znum = znum; j->z_lo = part.z_lo[k]; j->z_hi = part.z_hi[k];
 		j->idx32 = idx32; j->idx64 = idx64; j->nout = nout;
 		j->scores = scores; j->c1 = c1; j->c2 = c2;
-		j->rows = done - done_before;
-		for (int z = z_lo; z < z_next; z++) {
-			shard_of_z[z] = njobs;
-		}
-		njobs++;
+		j->rows = part.rows[k];
 	}
-	if (!whole && njobs > 0) {
+	if (!part.whole) {
 		/* the shards' lists: positions on the heap, indices and results in each plan's pinned buffer */
 		const size_t isz = idx32 != NULL ? sizeof(int) : sizeof(long long);
+		long long *pos[SXS_PART_MAX];
+		void *sub[SXS_PART_MAX];
 		for (int k = 0; k < njobs; k++) {
 			struct shard_job *j = &jobs[k];
 			j->compact = 1;
@@ -392,27 +232,12 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 			}
 			j->sub = buf;
 			j->out = (double *)(buf + sub_bytes);
+			pos[k] = j->pos;
+			sub[k] = j->sub;
 		}
-		long long *off_all = (long long *)calloc((size_t)nt * njobs, sizeof(long long));
-		CHECK_PTR(off_all);
-		for (int s = 0; s < njobs; s++) {
-			long long run = 0;
-			for (int k = 0; k < nt; k++) {
-				off_all[(size_t)k * njobs + s] = run;
-				for (int z = jobs[s].z_lo; z < jobs[s].z_hi; z++) {
-					run += pj[k].cnt[z];
-				}
-			}
-		}
-		for (int k = 0; k < nt; k++) {
-			pj[k].shard_of_z = shard_of_z; pj[k].off = off_all + (size_t)k * njobs; pj[k].jobs = jobs; pj[k].nshard = njobs;
-		}
-		run_threads(part_pass2, pj, nt);
-		free(off_all);
+		sxs_partition_fill(&part, pos, sub);
 	}
-	free(zdig);
-	free(cnt_all);
-	free(shard_of_z);
+	sxs_partition_free(&part);
 	if (njobs == 1) {
 		shard_main(&jobs[0]);
 	} else {
@@ -434,7 +259,6 @@ static void score_impl(double *scores, double *c1, double *c2, const int *idx32,
 			exit(EXIT_FAILURE);
 		}
 	}
-	free(per_z);
 	free(coefA);
 	free(coefB);
 	pthread_mutex_unlock(&g_score_lock);

@@ -508,6 +508,60 @@ def test_fit_headers_bitwise_live(fit_host, G):
 
 # ------------------------------------------------------------------ multi-rank plumbing (gloo, world size 2)
 
+def test_host_partition_of_a_pose_list_over_z_shards(capi):
+    """csrc/host/partition.c (what sxs_compute_saxs_scores does with several devices): contiguous z ranges with
+    balanced row counts; every row that lies on the z table lands in exactly one shard, in input order, with its own
+    index; rows off the table (negative, z digit beyond znum) land nowhere; 32- and 64-bit lists agree; one shard
+    leaves the list whole"""
+    lib = capi.lib()
+    IP, LLP = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)
+    lib.sxs_flat_partition_rows.restype = ctypes.c_int
+    lib.sxs_flat_partition_rows.argtypes = [IP, LLP, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, IP, IP, LLP,
+                                            LLP, LLP]
+    rng = np.random.default_rng(31)
+    L, znum = 15, 64
+    cell5 = (L + 1) ** 2 * (2 * L + 1) ** 3
+    for n, nsh, wide in ((300_000, 8, False), (300_000, 3, True), (1000, 8, False), (70_000, 64, False), (5, 4, True)):
+        z = rng.integers(0, znum, n)
+        z[rng.random(n) < 0.3] = 7                           # an overfull z step
+        idx = z.astype(np.int64) * cell5 + rng.integers(0, cell5, n)
+        idx[::97] = -1
+        idx[5::101] = (znum + 3) * cell5 + 11                # z digit off the table (fits int32 only when not wide)
+        if not wide:
+            idx[5::101] = min((znum + 3) * cell5 + 11, 2 ** 31 - 1)
+            idx = np.where(idx >= 2 ** 31, -1, idx)
+        valid = (idx >= 0) & (idx // cell5 < znum)
+        z_lo, z_hi = np.zeros(64, np.int32), np.zeros(64, np.int32)
+        rows = np.zeros(64, np.int64)
+        pos, sub = np.full(n, -7, np.int64), np.full(n, -7, np.int64)
+        a32 = None if wide else np.ascontiguousarray(idx.astype(np.int32))
+        a64 = np.ascontiguousarray(idx) if wide else None
+        ns = lib.sxs_flat_partition_rows(a32.ctypes.data_as(IP) if a32 is not None else None,
+                                         a64.ctypes.data_as(LLP) if a64 is not None else None, n, cell5, znum, nsh,
+                                         z_lo.ctypes.data_as(IP), z_hi.ctypes.data_as(IP), rows.ctypes.data_as(LLP),
+                                         pos.ctypes.data_as(LLP), sub.ctypes.data_as(LLP))
+        assert 1 <= ns <= nsh
+        assert z_lo[0] == 0 and z_hi[ns - 1] == znum and np.array_equal(z_lo[1:ns], z_hi[:ns - 1])   # contiguous cover
+        assert rows[:ns].sum() == valid.sum()
+        at = 0
+        zd = idx // cell5
+        for s in range(ns):
+            want = np.flatnonzero(valid & (zd >= z_lo[s]) & (zd < z_hi[s]))
+            assert rows[s] == len(want)
+            assert np.array_equal(pos[at:at + rows[s]], want)            # input order, exactly this shard's rows
+            assert np.array_equal(sub[at:at + rows[s]], idx[want])
+            at += rows[s]
+        if n >= 70_000 and nsh <= 8:
+            # balance: no shard above its fair share by more than the largest z step
+            per_z = np.bincount(zd[valid], minlength=znum)
+            assert rows[:ns].max() <= valid.sum() / ns + per_z.max()
+    # one shard: the list is not looked at
+    ns = lib.sxs_flat_partition_rows(a32.ctypes.data_as(IP) if a32 is not None else None, a64.ctypes.data_as(LLP) if a64 is not None else None,
+                                     n, cell5, znum, 1, z_lo.ctypes.data_as(IP), z_hi.ctypes.data_as(IP), rows.ctypes.data_as(LLP),
+                                     pos.ctypes.data_as(LLP), sub.ctypes.data_as(LLP))
+    assert ns == -1 and z_lo[0] == 0 and z_hi[0] == znum and rows[0] == n
+
+
 def test_z_sharding_covers_every_pose_once():
     from libfmftsaxs_b200 import dist as sd
     from libfmftsaxs_b200 import workload as wl
