@@ -9,6 +9,7 @@
  * the z steps over the visible B200s (SXS_CUDA_DEVICES).
  */
 #define _POSIX_C_SOURCE 200809L
+#include <pthread.h>
 #include <time.h>
 
 #include "common.h"
@@ -36,6 +37,31 @@ static void phase_done(const char *name)
 		printf("[phase] %-28s %.3f s\n", name, t - g_phase_t0);
 	}
 	g_phase_t0 = t;
+}
+
+/* ft + rm -> Euler side file -> grid indices on its own thread: it needs the two molecule centres only, so it runs
+ * beside the expansion of the molecules (SASA on host threads, CUDA start-up, K1), which it does not depend on. */
+struct ft_job {
+	const char *eul_path, *ft_path, *rm_path;
+	struct mol_vector3 ref_lig;
+	const double *zvals;
+	int znum, L;
+	long long nfast;
+	long long *index64;
+	int *ft_id, *order;
+};
+
+static void *ft_main(void *arg)
+{
+	struct ft_job *j = (struct ft_job *)arg;
+	/* The fast route reads the ft file once with all host threads and gives the same side file and the same indices as
+	 * the three passes of the reference (index.h); files it does not take go through those three passes. */
+	j->nfast = sxs_ft_file_to_indices(j->eul_path, j->ft_path, j->rm_path, &j->ref_lig, j->zvals, j->znum, j->L, 0, &j->index64,
+	                                  &j->ft_id, &j->order);
+	if (j->nfast < 0) {
+		sxs_ft_file2euler_file(j->eul_path, j->ft_path, j->rm_path, &j->ref_lig);
+	}
+	return NULL;
 }
 
 static void usage(void)
@@ -98,28 +124,32 @@ int main(int argc, char *argv[])
 	SXS_PRINTF("Reading receptor ...\n");
 	struct mol_vector3 coe, com;
 	struct mol_atom_group *rec = load_centred(rec_path, prms, 1, &coe);
-	struct sxs_spf_full *A = atom_grp2spf(rec, ff, qvals, qnum, L, 1);
 	SXS_PRINTF("Reading ligand ...\n");
 	struct mol_atom_group *lig = load_centred(lig_path, prms, 0, &com);
-	struct sxs_spf_full *B = atom_grp2spf(lig, ff, qvals, qnum, L, 1);
 
-	phase_done("PDB + SASA + expansion (K1)");
 	/* ligand centre relative to the receptor centre in the input frames (tools/correlate.c:108-113) */
 	struct mol_vector3 ref_lig;
 	MOL_VEC_SUB(ref_lig, com, coe);
 	MOL_VEC_MULT_SCALAR(ref_lig, ref_lig, -1.0);
-	/* ft + rm -> Euler side file -> grid indices.  The fast route reads the ft file once with all host threads and gives
-	 * the same side file and the same indices as the three passes of the reference (index.h); files it does not take
-	 * go through those three passes below. */
 	SXS_PRINTF("Converting FT and RM files into Euler coordinates ...\n");
-	long long *index64 = NULL;
-	int *ft_id = NULL, *order = NULL;
-	long long nfast = sxs_ft_file_to_indices(eul_path, ft_path, rm_path, &ref_lig, zvals, znum, L, 0, &index64, &ft_id, &order);
-	if (nfast < 0) {
-		sxs_ft_file2euler_file(eul_path, ft_path, rm_path, &ref_lig);
+	struct ft_job ftj = {eul_path, ft_path, rm_path, ref_lig, zvals, znum, L, -1, NULL, NULL, NULL};
+	pthread_t ft_thread;
+	const int ft_threaded = pthread_create(&ft_thread, NULL, ft_main, &ftj) == 0;
+	if (!ft_threaded) {
+		ft_main(&ftj);
 	}
 
-	phase_done("ft + rm -> Euler file + indices");
+	struct sxs_spf_full *A = atom_grp2spf(rec, ff, qvals, qnum, L, 1);
+	struct sxs_spf_full *B = atom_grp2spf(lig, ff, qvals, qnum, L, 1);
+	phase_done("PDB + SASA + expansion (K1)");
+	if (ft_threaded) {
+		pthread_join(ft_thread, NULL);
+	}
+	long long *index64 = ftj.index64;
+	int *ft_id = ftj.ft_id, *order = ftj.order;
+	const long long nfast = ftj.nfast;
+
+	phase_done("ft + rm -> Euler file + indices (rest)");
 	SXS_PRINTF("Reading experiment ...\n");
 	struct sxs_profile *exp_profile = sxs_profile_read(exp_path);
 	if (exp_profile == NULL) {
