@@ -419,3 +419,42 @@ def test_ft_rows_to_indices_on_the_device_equal_the_host_route():
     g30 = capi.cuda_ft_rows_to_indices(rot_id[:200000], trans[:200000], R, ref_lig, zvals, 30)
     ok30 = (w30 >= 0) | (g30 >= 0)
     assert np.array_equal(g30[ok30], w30[ok30]) and w30.max() > 2 ** 31
+
+
+@pytest.mark.parametrize("L,Q", [(3, 7), (6, 6), (9, 7), (17, 5)])
+def test_dense_scan_equals_the_list_path_at_other_orders(L, Q):
+    """the dense form of K3 is instantiated per range of L (lanes per pair, a2 pairs per lane, block size): at every one
+    of them the k best points of a dense scan carry the scores the LIST kernels give for the same indices, and 32- and
+    64-bit index lists give identical results (synthetic molecules: 120 + 60 atoms of the bench workload)"""
+    base = wl.make("cfg3_3k+1.5k_L15_Q50_70kx64z", nrot=1, nz=1)
+    rec, lig = base["rec"], base["lig"]
+    q = capi.mkarray(0.0, 0.4, Q)
+    nb, N = L + 1, 2 * L + 1
+    r, l = slice(0, 120), slice(0, 60)
+    A, _, _ = capi.expand(wl.MAP_PATH, rec["xyz"][r], rec["res"][r], rec["atm"][r], rec["radius"][r], q, L, sa=rec["sa"][r], water_mode=1)
+    B, _, _ = capi.expand(wl.MAP_PATH, lig["xyz"][l], lig["res"][l], lig["atm"][l], lig["radius"][l], q, L, sa=lig["sa"][l], water_mode=1)
+    eq = np.linspace(0.0, 0.45, 40)
+    ei = 1e4 * np.exp(-eq * eq * 60.0) + 50.0
+    a, scal = capi.opt_params(eq, ei, 0.03 * ei, q, 1.6)
+    plan = capi.Plan(L, q)
+    plan.set_molecules(A, B)
+    plan.set_translations(np.array([20.0, 21.0, 22.0]))
+    plan.set_experiment(a, scal[1], scal[2])
+    per_z = nb * nb * N ** 3
+    rng = np.random.default_rng(L)
+    idx = rng.integers(0, 3 * per_z, 400)
+    idx[::50] = -1                                   # rows that stay untouched
+    idx[1::50] = 5 * per_z                           # z digit off the table
+    s32 = plan.score(idx.astype(np.int32))
+    s64 = plan.score(idx.astype(np.int64))
+    assert all(np.array_equal(x, y) for x, y in zip(s32, s64)) and np.isfinite(s32[0]).all()
+    assert (s32[0][::50] == 0).all() and (s32[0][1::50] == 0).all() and (s32[0][2::50] > 0).all()
+    k = 16
+    ti, ts, tc1, tc2 = plan.scan_topk(k, z_lo=1, z_hi=2)
+    assert (ti >= per_z).all() and (ti < 2 * per_z).all() and len(np.unique(ti)) == k and np.all(np.diff(ts) >= 0)
+    ls, lc1, lc2 = plan.score(ti)
+    parity.check("dense scan vs list kernels, L = %d" % L, (ts, tc1, tc2), (ls, lc1, lc2))
+    sample = rng.integers(per_z, 2 * per_z, 20000)
+    ss, _, _ = plan.score(sample)
+    assert ss.min() >= ts[0] * (1 - 1e-9) and np.isin(sample[ss < ts[-1] * (1 - 1e-9)], ti).all()
+    plan.close()
