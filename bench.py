@@ -195,7 +195,9 @@ def run_reference(args):
     tot = sum(times)
     value = len(idx) * len(times) / tot
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+            # the CPU figure does not depend on the number of GPUs; the label follows the product arm's mode for this N
+            "scaling": (args.scaling if args.gpus > 1 else "weak"),
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "poses_in_sample": int(len(idx)), "cells_in_sample": int(len(np.unique(idx.astype(np.int64) // N ** 3))),
                        "L": L, "qnum": len(w["qvals"])},
