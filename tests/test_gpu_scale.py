@@ -298,7 +298,7 @@ def test_dense_scan_topk():
     """every grid point of one z step (16 x 16 cells x 31^3 = 7.6 M points) is scored on the device and
     the best 64 come back.  The scan runs the DENSE form of K3 (k_cross_dense: the inner sums of a (g1, g2) pair serve all
     31 values of a2); it must name the points the list form names (SXS_SCAN_LIST=1: the same scan through the list
-    kernels), carry what the list API gives for those indices to rounding, and its K3 must be >= 1.8x faster (measured
+    kernels), carry what the list API gives for those indices to rounding, and its K3 must be >= 1.5x faster (measured
     2.2x: 41 against 91 ms per z with the operands of every m staged in shared memory; 47 ms with plain loads)."""
     G = np.load(os.path.join(GOLD, "golden_4g9s.npz"))
     q, L = G["qvals"], int(G["L"])
@@ -324,7 +324,7 @@ def test_dense_scan_topk():
     plan.set_profiling(False)
     print("dense scan of one z: K3 %.1f ms dense form, %.1f ms list form; K4 %.1f / %.1f ms"
           % (t_dense["cross"][0], t_list["cross"][0], t_dense["fit"][0], t_list["fit"][0]))
-    assert t_dense["cross"][0] * 1.8 <= t_list["cross"][0]
+    assert t_dense["cross"][0] * 1.5 <= t_list["cross"][0]
     assert np.array_equal(np.sort(idx), np.sort(idx_l))
     o, ol = np.argsort(idx), np.argsort(idx_l)
     parity.check("dense form vs list form, top-%d" % k, (s[o], c1[o], c2[o]), (s_l[ol], c1_l[ol], c2_l[ol]))
@@ -458,3 +458,28 @@ def test_dense_scan_equals_the_list_path_at_other_orders(L, Q):
     ss, _, _ = plan.score(sample)
     assert ss.min() >= ts[0] * (1 - 1e-9) and np.isin(sample[ss < ts[-1] * (1 - 1e-9)], ti).all()
     plan.close()
+
+
+@pytest.mark.parametrize("L", [10, 20, 40])
+def test_config5_orders_against_reference(L):
+    """BASELINE config 5 sweeps lmax over 10, 15, 20, 30, 40: besides 15 (the goldens) and 30 (golden_l30) the orders 10,
+    20 and 40 against the compiled reference — 35 to 49 poses in two or three cells, one of them with >= 30 rows (the
+    reference's FFT branch), 32- and 64-bit lists; fixture by tests/golden/make_golden_cfg5.py with the reference's own
+    FMA-build answers as noise floor"""
+    F = np.load(os.path.join(GOLD, "golden_cfg5_orders.npz"))
+    g = lambda k: F["L%d_%s" % (L, k)]  # noqa: E731
+    q = g("qvals")
+    rec = wl.make_molecule(300, 100 + L)
+    lig = wl.make_molecule(150, 200 + L)
+    rec["xyz"] -= 0.5 * (rec["xyz"].min(0) + rec["xyz"].max(0))
+    lig["xyz"] -= lig["xyz"].mean(0)
+    A, _, _ = capi.expand(wl.MAP_PATH, rec["xyz"], rec["res"], rec["atm"], rec["radius"], q, L, sa=rec["sa"], water_mode=1)
+    B, _, _ = capi.expand(wl.MAP_PATH, lig["xyz"], lig["res"], lig["atm"], lig["radius"], q, L, sa=lig["sa"], water_mode=1)
+    for mine, ref in ((A, g("coefA_sample")), (B, g("coefB_sample"))):
+        assert np.max(np.abs(mine[:, ::7, ::53] - ref)) / np.abs(ref).max() < 1e-9
+    want = (g("scores"), g("c1"), g("c2"))
+    sens = (g("sens_scores"), g("sens_c1"), g("sens_c2"))
+    got = capi.scores(g("index"), A, B, g("a"), g("scal"), q, g("zvals"), L)
+    parity.check("config 5 order L = %d, %d poses" % (L, len(want[0])), got, want, sens=sens)
+    got64 = capi.scores(g("index").astype(np.int64), A, B, g("a"), g("scal"), q, g("zvals"), L)
+    assert all(np.array_equal(x, y) for x, y in zip(got, got64))
