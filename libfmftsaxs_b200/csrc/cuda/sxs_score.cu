@@ -499,7 +499,6 @@ k_translate_rt(int L, int qnum, int nz, const int *__restrict__ slab_flag, const
 	const bool in_a = tile < tiles_a;
 	const int n = in_a ? nla : nlb;                               /* rows = columns of this order's T block */
 	const int r0 = SXS_TR_ROWS * (in_a ? tile : tile - tiles_a); /* first row of the tile inside its order */
-	const double2 *tblk = sT + (in_a ? 0 : nla * nla);
 	const double2 *bcol = sB + (in_a ? 0 : nla * N);
 	const int mlrow0 = (in_a ? mla : mlb) + r0;
 	const bool has_g1 = g1 < N;
@@ -509,21 +508,47 @@ k_translate_rt(int L, int qnum, int nz, const int *__restrict__ slab_flag, const
 		rr[k] = (r0 + k < n) ? r0 + k : n - 1; /* rows past the block repeat the last one and are not stored */
 	}
 
-	for (int zl = 0; zl < nz; zl++) {
-		if (!slab_flag[zl * nb + b2]) {
-			continue;
-		}
-		__syncthreads();
+	/* The two T blocks of a z step are copied into one of two shared-memory stages (cp.async) while the step before it
+	 * is computed: with a synchronous staging loop per z, 20 % of the stall samples at L = 30 sat on the long scoreboard
+	 * (the T table misses L2 behind the stream of St stores) and 21 % on the two barriers per z (r2ai ncu).  One barrier
+	 * per z is left: it publishes the landed stage and retires the one the next copy overwrites. */
+	const int tsz = nla * nla + nlb * nlb;
+	auto t_stage = [&](int zl, double2 *stg) {
 		const double2 *tsrc = T + ((size_t)zl * qnum + q) * nb * nb * nb;
 		for (int e = threadIdx.x; e < nla * nla; e += blockDim.x) {
 			const int r = e / nla, j = e - r * nla;
-			sT[e] = tsrc[((size_t)ma * nb + ma + r) * nb + ma + j];
+			const unsigned dsta = (unsigned)__cvta_generic_to_shared(stg + e);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsta), "l"(tsrc + ((size_t)ma * nb + ma + r) * nb + ma + j) : "memory");
 		}
 		for (int e = threadIdx.x; e < nlb * nlb; e += blockDim.x) {
 			const int r = e / nlb, j = e - r * nlb;
-			sT[nla * nla + e] = tsrc[((size_t)mb * nb + mb + r) * nb + mb + j];
+			const unsigned dstb = (unsigned)__cvta_generic_to_shared(stg + nla * nla + e);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstb), "l"(tsrc + ((size_t)mb * nb + mb + r) * nb + mb + j) : "memory");
 		}
-		__syncthreads();
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	};
+	int zl = 0;
+	while (zl < nz && !slab_flag[zl * nb + b2]) {
+		zl++;
+	}
+	int stage = 0;
+	if (zl < nz) {
+		t_stage(zl, sT);
+	}
+	for (; zl < nz;) {
+		int zn = zl + 1;
+		while (zn < nz && !slab_flag[zn * nb + b2]) {
+			zn++;
+		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncthreads(); /* this z's blocks (and, first time, the B rows) are in place; everybody is done with the previous z */
+		if (zn < nz) {
+			t_stage(zn, sT + (stage ^ 1) * tsz);
+		}
+		const double2 *tblk = sT + stage * tsz + (in_a ? 0 : nla * nla);
+		const int zcur = zl;
+		zl = zn;
+		stage ^= 1;
 		if (!active) {
 			continue;
 		}
@@ -546,13 +571,14 @@ k_translate_rt(int L, int qnum, int nz, const int *__restrict__ slab_flag, const
 				im[k][1] = __dadd_rn(im[k][1], __fma_rn(t.x, bB.y, -__dmul_rn(t.y, bB.x)));
 			}
 		}
-		double2 *dst = St + ((((size_t)zl * nb + b2) * qnum + q) * 3 + c) * ML * NP;
+		double2 *dst = St + ((((size_t)zcur * nb + b2) * qnum + q) * 3 + c) * ML * NP;
 #pragma unroll
 		for (int k = 0; k < SXS_TR_ROWS; k++) {
 			if (r0 + k < n) {
-				dst[(size_t)(mlrow0 + k) * NP + g0] = make_double2(re[k][0], im[k][0]);
+				/* streaming stores: St is read back by K3 from HBM anyway (10 GB per group) and must not push T out of L2 */
+				__stcs(&dst[(size_t)(mlrow0 + k) * NP + g0], make_double2(re[k][0], im[k][0]));
 				if (has_g1) {
-					dst[(size_t)(mlrow0 + k) * NP + g1] = make_double2(re[k][1], im[k][1]);
+					__stcs(&dst[(size_t)(mlrow0 + k) * NP + g1], make_double2(re[k][1], im[k][1]));
 				}
 			}
 		}
@@ -977,7 +1003,8 @@ static int launch_translate(sxs_cuda_plan *p, int zspan, const int *d_zlist, cud
 	SXS_CK_LAUNCH();
 	{
 		const int npair = (L + 2) / 2, rows = L + 2;
-		const size_t shm_t = sizeof(double2) * ((size_t)rows * N + (size_t)nb * nb + 1);
+		/* the B rows of the block's two orders + two stages of its T blocks (nla^2 + nlb^2 <= nb^2 + 1 elements each) */
+		const size_t shm_t = sizeof(double2) * ((size_t)rows * N + 2 * ((size_t)nb * nb + 1));
 		const int GH = (N + 1) / 2;
 		int max_tiles = 0;
 		for (int ma = 0; ma < npair; ma++) {
