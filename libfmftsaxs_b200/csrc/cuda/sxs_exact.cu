@@ -99,16 +99,17 @@ __device__ __forceinline__ void fit_store(const struct lq_state *st, double *__r
  * two passes, src/min_saxs.c:261-319 and :3-105).  The row is streamed from L2/HBM through a per-lane ring in shared
  * memory with 16-byte asynchronous copies (cp.async, three per node), SXS_FIT_RING - 1 nodes ahead of the arithmetic.
  * A node is straight-line code: exp through its core without the range test, the pass-1 quotient through the
- * reciprocal table (both bit-exact, fit_eval.h) — 300 executed instructions per node and evaluation against 362 for
- * the form with the two range branches (r2n / r2r ncu).
+ * reciprocal table (both bit-exact, fit_eval.h) — 323 executed instructions per node and evaluation (127 + 196) against
+ * 362 for the form with the two range branches, no branch and no spill in either loop (r2n / r2s ncu).
  *
- * Measured and not kept (profiles/r2_k4_notes.md, r2o-r2r): two or three nodes per trip (SXS_FIT_NPI; the fixed-latency
- * "wait" share of the objective's stall samples falls from 45 % to 21 %, but the trip needs ~60 more registers inside a
- * kernel that is at 255: its spills cost what the interleaving wins; variants/ builds of r2o-r2q), rows prefetched through registers instead of the
- * ring (32 lanes = 32 cache lines per load: L1 thrashes), G(c1, q_i) kept in shared memory for pass 2 (one exp
- * per node less, but 100 KB less L1 for the kernel's spills), the optimiser's matrices parked in shared memory
- * across the objective, G of node i + 1 formed during node i.  Every one of them lands within 57-72 ms per 1.12 M fits
- * against 55 for this form and 63 for the form before it.
+ * Measured and not kept (profiles/r2_k4_notes.md, r2o-r2ae; none of these is left in the code): two to four nodes per
+ * trip (the fixed-latency "wait" share of the objective's stall samples falls from 45 % to 21 %, but a trip needs ~60
+ * more registers inside a kernel that is at 255: its spills cost what the interleaving wins), rows prefetched through
+ * registers instead of the ring (32 lanes = 32 cache lines per load: L1 thrashes), G(c1, q_i) kept in shared memory for
+ * pass 2 (one exp per node less, but 100 KB less L1 for the kernel's spills), the optimiser's matrices parked in
+ * shared memory across the objective, G of node i + 1 formed during node i, the six terms of node i + 1 carried in
+ * registers.  Every one of them lands within 57-72 ms per 1.12 M fits against 55 for this form and 63 for the form
+ * before it.
  *
  * The iteration boundary (part B: BFGS update, Cauchy point, subspace step) runs when NUM/DEN of the warp's waiting
  * lanes wait for it, so that it executes with most lanes active. */
