@@ -8,10 +8,11 @@
  *   k_self_terms     six self cross terms of one molecule (src/min_saxs.c:437-499)
  *   k_profile        I(q) of one molecule (src/profile.c:186-233)
  *
- * K4: per objective evaluation a thread makes one pass over its 6*qnum cross terms (one exp per node,
- * sxs_fit_eval_fused); 7-13 evaluations per fit on real data, ~20 on the synthetic bench workload.  Build
- * with -DSXS_FIT_EVAL_EXACT for the reference's two-pass objective (bit-identical to it: exp() is the reference
- * libm's algorithm, exp_glibc.h).
+ *   k_ft_rows_to_index   ft rows -> flat grid indices (src/index.c:38-75,114, tools/correlate.c:214-247)
+ *
+ * K4 evaluates the objective as the reference does — two passes over the 6*qnum cross terms of the point per
+ * evaluation, exp() by the reference libm's algorithm (exp_glibc.h) — and is bit-identical to the vendored L-BFGS-B on
+ * equal cross terms; 7-13 evaluations per fit on real data, ~20 on the synthetic bench workload.
  */
 #include <math.h>
 
@@ -19,13 +20,9 @@
 
 #define SXS_HD __host__ __device__ __forceinline__
 #define SXS_ROWMAJOR_VEC 1
-/* The objective is the reference's two-pass form (sxs_fit_eval), bit-identical to it.  -DSXS_FIT_EVAL_FUSED builds the
- * one-pass form of round 1 (algebraically equal, 27 % cheaper per evaluation): on the real 4G9S list it leaves 17 of
- * 1131 / 45 of 70 000 rows beyond 1e-6 in c2 against 3 / 10 for the two-pass form (gpurun_out/r2a_pytest_*.txt), so
- * it is not what ships. */
-#ifdef SXS_FIT_EVAL_FUSED
-#define SXS_FIT_RQ_TABLE 1     /* reciprocal node spacings from shared memory */
-#endif
+/* The one-pass form of round 1 (sxs_fit_eval_fused in fit_eval.h: algebraically equal, 27 % cheaper per evaluation)
+ * left 17 of 1131 / 45 of 70 000 real 4G9S rows beyond 1e-6 in c2 against 3 / 10 for the two-pass form
+ * (gpurun_out/r2a_pytest_*.txt): the kernel does not offer it any more. */
 #include "fit_point.h"
 
 #ifndef SXS_FIT_THREADS
