@@ -51,19 +51,17 @@ SXS_HD void sxs_fit_point_ex(const double *x, long stride, long qstride, const d
 	ctx.scale = 1.0;
 	ctx.scale = sxs_fit_rescale(&ctx, peak);
 
-	const double sum_a0 = sxs_fit_sum_a0(a, qnum);
-	(void)sum_a0;
 #ifdef SXS_FIT_GENERIC_LBFGSB
 	struct lb_state st;
 	lb_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT, SXS_C1_LOWER, SXS_C1_UPPER, SXS_C2_LOWER, SXS_C2_UPPER, 1e+7);
 	while (lb_step(&st, 1e-5) == LB_NEED_EVAL) {
-		SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+		SXS_FIT_EVAL(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 	}
 #else
 	struct lq_state st;
 	lq_begin(&st, SXS_C1_DEFAULT, SXS_C2_DEFAULT);
 	while (lq_step(&st, SXS_FIT_PGTOL, SXS_FIT_TOL) == LQ_NEED_EVAL) {
-		SXS_FIT_EVAL(&ctx, sum_a0, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
+		SXS_FIT_EVAL(&ctx, st.x[1], st.x[2], &st.f, &st.g[1], &st.g[2]);
 	}
 #endif
 	*score = sqrt(st.f);

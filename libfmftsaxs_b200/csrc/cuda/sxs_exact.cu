@@ -20,7 +20,7 @@
 
 #define SXS_HD __host__ __device__ __forceinline__
 #define SXS_ROWMAJOR_VEC 1
-/* The one-pass form of round 1 (sxs_fit_eval_fused in fit_eval.h: algebraically equal, 27 % cheaper per evaluation)
+/* The one-pass form of round 1 (algebraically equal, 27 % cheaper per evaluation; see fit_eval.h)
  * left 17 of 1131 / 45 of 70 000 real 4G9S rows beyond 1e-6 in c2 against 3 / 10 for the two-pass form
  * (gpurun_out/r2a_pytest_*.txt): the kernel does not offer it any more. */
 #include "fit_point.h"
