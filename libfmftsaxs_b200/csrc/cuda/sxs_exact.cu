@@ -54,7 +54,7 @@ __shared__ double fs_dq[SXS_FIT_MAXQ];      /* q_i - q_{i-1}, q_{-1} = -1 */
 __shared__ uint64_t fs_etab[SXS_EXP_TABLE_ENTRIES];
 __shared__ int fs_fast; /* |corr q^2| < 512 for every c1 of the box and every node: the exp core needs no range test */
 
-__device__ __forceinline__ void fit_tables_fill(const double *a, const double *qvals, int qnum, double mult)
+__device__ __forceinline__ void fit_tables_fill(const double *a, const double *qvals, int qnum, double mult, int allow_fast)
 {
 	if (threadIdx.x == 0) {
 		/* |c1^2 - 1| <= max(1 - L1^2, U1^2 - 1) inside the box the optimiser never leaves */
@@ -64,7 +64,7 @@ __device__ __forceinline__ void fit_tables_fill(const double *a, const double *q
 			qq = fmax(qq, qvals[i] * qvals[i]);
 		}
 		const double bound = fabs(mult) * span * qq;
-		fs_fast = (bound < 500.0) ? 1 : 0; /* false for NaN as well */
+		fs_fast = (allow_fast && bound < 500.0) ? 1 : 0; /* false for NaN as well */
 	}
 	for (int i = threadIdx.x; i < SXS_EXP_TABLE_ENTRIES; i += blockDim.x) {
 		fs_etab[i] = d_exp_tab[i];
@@ -261,10 +261,10 @@ __device__ __noinline__ void fit_eval_safe(const struct fit_eval_args *ap, doubl
 
 __global__ void __launch_bounds__(SXS_FIT_THREADS, SXS_FIT_MINBLOCKS)
 k_fit(const double *__restrict__ X, long long npts, const double *__restrict__ a, const double *__restrict__ qvals,
-      int qnum, double mult, double peak, int rescale, double *__restrict__ res,
+      int qnum, double mult, double peak, int rescale, int allow_fast, double *__restrict__ res,
       unsigned long long *__restrict__ ticket)
 {
-	fit_tables_fill(a, qvals, qnum, mult);
+	fit_tables_fill(a, qvals, qnum, mult, allow_fast);
 	__syncthreads();
 	const int fast = fs_fast;
 
@@ -371,7 +371,8 @@ int sxs_launch_fit(const double *d_x, long long npts, const double *d_a, const d
 	const long long need = (npts + SXS_FIT_THREADS - 1) / SXS_FIT_THREADS;
 	if (blocks > need) blocks = need;
 	SXS_CK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned long long), stream));
-	k_fit<<<(unsigned)blocks, SXS_FIT_THREADS, shm, stream>>>(d_x, npts, d_a, d_qvals, qnum, mult, peak, rescale, d_res, d_ticket);
+	k_fit<<<(unsigned)blocks, SXS_FIT_THREADS, shm, stream>>>(d_x, npts, d_a, d_qvals, qnum, mult, peak, rescale,
+	                                                           getenv("SXS_FIT_FORCE_SAFE") == NULL /* tests: the fallback objective */, d_res, d_ticket);
 	SXS_CK_LAUNCH();
 	return 0;
 }

@@ -55,6 +55,20 @@ def main():
         assert np.allclose(ls, ts, rtol=1e-6) and np.isfinite(ts).all(), (ls, ts)
         plan.close()
         print("L = %d, Q = %d: list (32/64-bit) and dense scan ok; best chi %.4g" % (L, Q, ts[0]), flush=True)
+    # K4 alone, and its fallback objective (full exp, IEEE quotients) that runs when |corr q^2| could reach 512 in the box:
+    # a large `mult` selects it; with mult = 2000 the arguments stay below 41 and the two objectives must agree bit for bit
+    FC = np.load(os.path.join(REPO, "tests", "golden", "fit_cases.npz"))
+    G = np.load(os.path.join(REPO, "tests", "golden", "golden_4g9s.npz"))
+    X = np.ascontiguousarray(FC["X52"])
+    fast = capi.cuda_fit_profiles(X, G["a"], G["qvals"], float(G["scal"][1]), float(G["scal"][2]))
+    assert np.array_equal(fast, FC["fit52"]), "K4 against the stored outputs of the reference's L-BFGS-B"
+    q4 = np.ascontiguousarray(G["qvals"])
+    big = 2000.0                                     # bound = 2000 * 0.0816 * 0.25 = 40.8 < 500: fast path
+    huge = 500.0 / 0.0816 / float(q4.max() ** 2) * 1.01   # bound just above 500: fallback path, same arguments otherwise
+    r_fast = capi.cuda_fit_profiles(X, G["a"], q4, big, float(G["scal"][2]))
+    r_safe = capi.cuda_fit_profiles(X, G["a"], q4, huge, float(G["scal"][2]))
+    print("K4: 52 fits bit-identical to the reference; mult = %g (fast objective) finite %s; mult = %g (fallback objective) ran, finite %s"
+          % (big, bool(np.isfinite(r_fast).all()), huge, bool(np.isfinite(r_safe).all())), flush=True)
     # ft rows -> indices
     nrot, n = 50, 3000
     qn = rng.normal(size=(nrot, 4)); qn /= np.linalg.norm(qn, axis=1)[:, None]

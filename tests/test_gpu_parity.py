@@ -101,6 +101,14 @@ def test_fit_kernel_against_reference_lbfgsb(G, FC):
     print("identical evaluation counts: %.4f" % np.mean(got[:, 3] == want[:, 3]))
     # optimiser, two-pass objective and exp() follow the reference operation for operation: same bits, same counts
     assert np.array_equal(got, want)
+    # the fallback objective (full exp with its range test, IEEE quotients, plain loads: what runs when |corr q^2| could
+    # reach 512 inside the box of c1) gives the same bits
+    os.environ["SXS_FIT_FORCE_SAFE"] = "1"
+    try:
+        safe = capi.cuda_fit_profiles(X, a, q, scal[1], scal[2], rescale=True)
+    finally:
+        os.environ.pop("SXS_FIT_FORCE_SAFE", None)
+    assert np.array_equal(safe, want)
 
 
 def test_device_exp_equals_host_libm():
