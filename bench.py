@@ -440,7 +440,7 @@ def pose_list_stats(idx, L):
             "rows_per_cell_max": int(counts.max())}
 
 
-TRAFFIC_FILE = "profiles/r2ac_ncu_traffic.json"
+TRAFFIC_FILE = "profiles/r2al_ncu_traffic.json"
 
 
 def hbm_peak():
