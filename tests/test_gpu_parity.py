@@ -150,6 +150,27 @@ def test_scores_z40_ref_chi(G):
     assert np.max(np.abs(c2 - rc[:, 3])) < 1e-3
 
 
+def test_sasa_restatement_error_bounds_the_score_drift(G):
+    """libmol2's accs is restated (csrc/host/mol2_mini.c) and leaves the W coefficients of ref_spf within 1e-5 of their
+    scale, a few hundred near-zero ones up to 22 % relative (test_expand_ref_spf_golden).  What such an error does to the
+    result: the SASA fractions of both molecules are perturbed by 1e-3 relative per atom (100 x the observed error in W)
+    and the 52 golden poses are rescored from the atoms — chi, c1, c2 move by less than 1e-3 relative"""
+    q, L = G["qvals"], int(G["L"])
+    rng = np.random.default_rng(17)
+    out = []
+    for eps in (0.0, 1e-3):
+        coef = []
+        for mol in ("rec", "lig"):
+            sa = G[mol + "_sa"] * (1.0 + eps * rng.uniform(-1.0, 1.0, len(G[mol + "_sa"])))
+            c, _, _ = capi.expand(MAP, G[mol + "_xyz"], names(G[mol + "_res"]), names(G[mol + "_atm"]), G[mol + "_radius"], q, L,
+                                  sa=sa, water_mode=1)
+            coef.append(c)
+        out.append(capi.scores(G["z40_index"], coef[0], coef[1], G["a"], G["scal"], q, [40.0], L))
+    ds, d1, d2 = parity.deviations(out[1], out[0])
+    print("SASA perturbed by 1e-3: max relative drift chi %.2e c1 %.2e c2 %.2e" % (ds.max(), d1.max(), d2.max()))
+    assert max(ds.max(), d1.max(), d2.max()) < 1e-3
+
+
 def test_scores_six_z_with_fft_branch_cells(G):
     """1131 real rows over 6 z steps; some cells hold >= 30 rows (the reference's FFTW branch)"""
     q, L = G["qvals"], int(G["L"])
